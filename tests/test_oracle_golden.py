@@ -1,0 +1,155 @@
+"""Pins the oracle against outputs of the reference itself (tests/golden/*.npz, produced
+by tests/golden/make_golden.py from /root/reference) and against closed-form invariants
+implied by the reference code."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dsin_oracle as O
+from oracle import ms_ssim_oracle as M
+
+
+def test_mask_matches_reference_full_small(golden_dir):
+    g = np.load(os.path.join(golden_dir, "mask_golden.npz"))
+    for (H, W) in ((80, 144), (120, 96)):
+        ref = g["full_%dx%d" % (H, W)][0]  # (h, w, P)
+        mine = O.gaussian_masks(H, W, 20, 24)  # (P, h, w)
+        assert mine.dtype == np.float32
+        assert np.array_equal(np.transpose(mine, (1, 2, 0)), ref)
+
+
+@pytest.mark.parametrize("hw", [(320, 1224), (320, 960)])
+def test_mask_matches_reference_sampled_full_size(golden_dir, hw):
+    H, W = hw
+    g = np.load(os.path.join(golden_dir, "mask_golden.npz"))
+    mine = O.gaussian_masks(H, W, 20, 24)
+    assert tuple(g["shape_%dx%d" % hw]) == (mine.shape[1], mine.shape[2], mine.shape[0])
+    idx = g["idx_%dx%d" % hw]
+    assert np.array_equal(mine[idx[:, 0], idx[:, 1], idx[:, 2]], g["val_%dx%d" % hw])
+    am = mine.reshape(mine.shape[0], -1).argmax(1)
+    assert np.array_equal(am, g["argmax_%dx%d" % hw])
+    # the prior peaks at (top+1, left+1)
+    w = mine.shape[2]
+    assert (am[0] // w, am[0] % w) == (1, 1)
+    assert (am[1] // w, am[1] % w) == (1, 25)
+
+
+def test_msssim_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "msssim_golden.npz"))
+    for k in (0, 1):
+        img, rec = g["img_%d" % k], g["rec_%d" % k].astype(np.float32)
+        assert M.msssim_standard(img, rec) == pytest.approx(float(g["std_%d" % k]), abs=1e-7)
+        assert M.msssim_reference_call(img, rec) == pytest.approx(float(g["utils_%d" % k]), abs=1e-7)
+
+
+def test_same_padding_rules():
+    assert O.same_pads(320, 5, 2) == (1, 2)
+    assert O.same_pads(320, 3, 2) == (0, 1)
+    assert O.same_pads(306, 3, 1) == (1, 1)
+    assert O.same_pads(1224, 3, 1, 128) == (128, 128)
+
+
+def test_transposed_conv_is_adjoint_of_same_conv():
+    """conv2d_transpose(SAME, s=2) == autograd adjoint of the SAME s=2 conv."""
+    rng = np.random.default_rng(0)
+    for k in (3, 5):
+        w = rng.standard_normal((k, k, 4, 6)).astype(np.float64)  # [k,k,out(=4),in(=6)]
+        q = torch.tensor(rng.standard_normal((1, 6, 5, 7)))
+        x = torch.zeros(1, 4, 10, 14, dtype=torch.float64, requires_grad=True)
+        y = O.conv2d_same(x, w, stride=2)  # HWIO with I=4 (x channels), O=6
+        (g,) = torch.autograd.grad(y, x, grad_outputs=q)
+        mine = O.conv2d_transpose_same_s2(q, w)
+        assert torch.allclose(mine, g, atol=1e-12)
+
+
+def test_quantizer_picks_nearest_centre_first_index():
+    c = np.array([0.5, -1.0, 0.5, 2.0], dtype=np.float32)
+    z = torch.tensor([[[[0.5, -0.9, 1.9, 0.6]]]])
+    qbar, qsoft, qhard, sym = O.quantize(z, c)
+    assert sym.dtype == torch.int64
+    assert sym.flatten().tolist() == [0, 1, 3, 0]  # duplicate centre -> first index
+    assert torch.allclose(qhard.flatten(), torch.tensor([0.5, -1.0, 2.0, 0.5]))
+    assert torch.allclose(qbar, qhard, atol=1e-6)
+
+
+def test_heatmap_zero_gives_constant_symbol():
+    W = {O.ENC + "centers": np.array([0.7, -0.2, 1.5, -1.1, 0.1, 2.0], dtype=np.float32)}
+    z33 = torch.randn(1, 33, 4, 5)
+    z33[:, 0] = -100.0  # sigmoid -> 0 -> heatmap3D == 0
+    hm = O.heatmap3d(z33)
+    assert float(hm.abs().max()) == 0.0
+    _, _, _, sym = O.quantize(hm * z33[:, 1:], W[O.ENC + "centers"])
+    assert (sym == 4).all()  # argmin |c_j| = 0.1
+
+
+def test_patch_tiling_roundtrip():
+    img = torch.arange(40 * 48 * 3, dtype=torch.float32).reshape(40, 48, 3)
+    p = O.extract_patches(img, 20, 24)
+    assert p.shape == (4, 20, 24, 3)
+    assert torch.equal(p[1], img[0:20, 24:48])
+    assert torch.equal(O.fold_patches(p, 40, 48), img)
+
+
+def test_sifinder_identity_pair_finds_own_origin():
+    """y == x: Pearson == 1 at the patch origin; the mask peak sits at origin+(1,1), so
+    the argmax is at the origin or within one pixel of it."""
+    from dsin_b200 import synth
+    x, _ = synth.make_pair(3, 80, 144, sigma=2.0, disparity=0, noise=0.0)
+    xt = torch.tensor(x)[None]
+    y_syn, row, col, best = O.si_full_img(xt, xt, xt)
+    P = row.shape[1]
+    for p in range(P):
+        pr, pc = (p // 6) * 20, (p % 6) * 24
+        assert abs(int(row[0, p]) - pr) <= 1 and abs(int(col[0, p]) - pc) <= 1
+    assert float(best.min()) > 0.99
+
+
+def test_probclass_is_causal():
+    from dsin_b200 import synth
+    W = synth.make_weights(1)
+    rng = np.random.default_rng(0)
+    c = W[O.ENC + "centers"]
+    sym = torch.tensor(rng.integers(0, 6, (1, 8, 6, 7)))
+    q = torch.tensor(c)[sym]
+    b0 = O.probclass_bitcost(q, sym, W)
+    # change one voxel: only voxels at or after it in (C,H,W) raster order may change
+    sym2 = sym.clone()
+    sym2[0, 3, 2, 4] = (sym2[0, 3, 2, 4] + 1) % 6
+    q2 = torch.tensor(c)[sym2]
+    b1 = O.probclass_bitcost(q2, sym2, W)
+    changed = (b0 != b1)[0]
+    order = torch.arange(8 * 6 * 7).reshape(8, 6, 7)
+    assert changed.any()
+    assert int(order[changed].min()) >= int(order[3, 2, 4])
+
+
+def test_sinet_identity_init_passes_channels_through():
+    """src/siNet.py:13-20: identity-initialised 3x3 layers copy their input channels."""
+    W = {}
+    cin = 6
+    for i in range(9):
+        w = np.zeros((3, 3, cin, 32), dtype=np.float32)
+        for c in range(cin):
+            w[1, 1, c, c] = 1
+        W[O.SIN + "g_conv%d/weights" % (i + 1)] = w
+        W[O.SIN + "g_conv%d/biases" % (i + 1)] = np.zeros(32, dtype=np.float32)
+        cin = 32
+    last = np.zeros((1, 1, 32, 3), dtype=np.float32)
+    for c in range(3):
+        last[0, 0, c, c] = 1
+    W[O.SIN + "g_conv_last/weights"] = last
+    W[O.SIN + "g_conv_last/biases"] = np.zeros(3, dtype=np.float32)
+    x = torch.rand(1, 6, 16, 20) + 0.1  # positive: lrelu is the identity
+    out = O.si_net(x, W)
+    assert torch.allclose(out, x[:, :3], atol=1e-6)
+
+
+def test_crop_and_resize_coordinates():
+    """sampling coordinates for row 100 of a 320-row image."""
+    y = np.tile(np.arange(320, dtype=np.float32)[:, None, None], (1, 1224, 3))
+    out = O.crop_and_resize_patches(y, [100], [0], 20, 24)
+    assert out[0, 0, 0, 0] == pytest.approx(99.6875, abs=1e-4)
+    assert out[0, 1, 0, 0] == pytest.approx(100.7368, abs=1e-3)
+    assert out[0, 2, 0, 0] == pytest.approx(101.7862, abs=1e-3)
