@@ -1,0 +1,191 @@
+"""AE facade (/root/reference/src/AE.py) on libdsin_b200: same constructor and inference methods.
+
+    AE(ae_config, pc_config, encoder, decoder, siFinder, SI_full_img, siNet, cur_dir)
+    siNet_get_reconstructed(x, y) -> (y_dec, y_syn, x_dec, x_with_si, bpp)     src/AE.py:132-148
+    create_y_dec(y)                                                            src/AE.py:150-152
+    load_model(path) / save_model(path)                                        src/AE.py:154-175
+
+Differences (documented in DESIGN.md): inputs may hold B >= 1 pairs (the reference's SI path is
+hard-wired to batch 1, src/AE.py:26) -- each pair is processed with batch-1 semantics and bpp is
+the batch aggregate of bits.bitcost_to_bpp; the two autoencoder passes (on y and on x) run as
+one batch of 2B images; weights live in an .npz keyed by the TF variable names; training entry
+points raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import autoencoder_imgcomp as autoencoder
+from . import bits_imgcomp as bits
+from . import ops
+from . import probclass_imgcomp as probclass
+from . import synth
+from .siFinder import GaussianPrior
+
+
+class AE(object):
+    def __init__(self, ae_config, pc_config, encoder, decoder, siFinder, SI_full_img, siNet, cur_dir,
+                 weights=None, seed=0, device=None):
+        self.ae_config = ae_config
+        self.pc_config = pc_config
+        self._encode = encoder
+        self._decode = decoder
+        self.AE_only = self.ae_config.AE_only
+        self.si_weight = 0.0 if self.AE_only else self.ae_config.si_weight
+        self._siNet = siNet
+        self._SI_full_img = SI_full_img
+        self._siFinder = siFinder
+        self.use_y_gauss_mask = self.ae_config.use_gauss_mask
+        self._batch_size = self.ae_config.batch_size if self.AE_only else 1
+        self._input_dim_h, self._input_dim_w = self.ae_config.crop_size
+        self._y_patch_h, self._y_patch_w = self.ae_config.y_patch_size
+        try:  # the reference opens the train list at construction (src/AE.py:29); absent at inference
+            with open(os.path.join(cur_dir or "", ae_config.file_path_train)) as f:
+                self.num_training_imgs = sum(1 for _ in f) // 2
+        except (OSError, TypeError):
+            self.num_training_imgs = 0
+        if getattr(self.ae_config, "normalization", "FIXED") not in ("FIXED",):
+            raise ValueError("Invalid normalization style {} (only FIXED is built)".format(
+                self.ae_config.normalization))
+        if not getattr(self.ae_config, "heatmap", True):
+            raise NotImplementedError("heatmap=False is not built")
+
+        ops.handle(device)  # fails loudly without libdsin_b200.so / an sm_100 GPU
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.ae_imgcomp = autoencoder.get_network_cls(self.ae_config)(self.ae_config)
+        self.pc_imgcomp = probclass.get_network_cls(self.pc_config)(self.pc_config,
+                                                                    num_centers=self.ae_config.num_centers)
+        self.mask = self.create_gaussian_masks() if self.use_y_gauss_mask else 1
+        self.weights = None
+        self.set_weights(weights if weights is not None else synth.make_weights(seed))
+        self._pinned = {}
+        self._ring = 0
+        self.last = {}
+
+    # ------------------------------------------------------------------ weights
+    def set_weights(self, W):
+        """W: dict keyed by TF variable names."""
+        self.weights = W
+        self.ae_imgcomp.load_weights(W)
+        self.pc_imgcomp.load_weights(W)
+        if not self.AE_only:
+            self._siNet.load_weights(W)
+
+    def save_model(self, save_path):
+        path = save_path if save_path.endswith(".npz") else save_path + ".npz"
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        synth.save_weights(path, self.weights)
+
+    def load_model(self, load_path):
+        path = load_path if load_path.endswith(".npz") else load_path + ".npz"
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                "{} not found.  dsin_b200 reads weights from an .npz keyed by the TF variable names; "
+                "a TF-V2 checkpoint importer is not built yet (SURVEY 8f N1)".format(path))
+        print("Loading " + path)
+        self.set_weights(synth.load_weights(path))
+
+    # ------------------------------------------------------------------ helpers kept from the reference
+    def create_gaussian_masks(self):
+        """The reference returns a (1,h,w,P) float32 constant (1.18 GB at 320x1224); the kernels
+        evaluate the same prior analytically, so only its geometry is returned."""
+        return GaussianPrior(self._input_dim_h, self._input_dim_w, self._y_patch_h, self._y_patch_w)
+
+    @staticmethod
+    def get_mean_var():
+        mean = np.array([93.70454143384742, 98.28243432206516, 94.84678088809876], dtype=np.float32)
+        var = np.array([5411.79935676, 5758.60456747, 5890.31451232], dtype=np.float32)
+        return mean.reshape(3, 1, 1), var.reshape(3, 1, 1)
+
+    def siNet_update(self, x, y):
+        raise NotImplementedError("training is out of scope for dsin_b200 (inference hot path only)")
+
+    def siNet_validate(self, x, y):
+        raise NotImplementedError("training is out of scope for dsin_b200 (inference hot path only)")
+
+    # ------------------------------------------------------------------ host <-> device staging
+    def _to_device(self, a, slot):
+        if torch.is_tensor(a):
+            if a.is_cuda:
+                return a.to(torch.float32).contiguous()
+            return a.to(self.device, non_blocking=True).to(torch.float32)
+        a = np.ascontiguousarray(a)
+        key = (slot, a.shape, a.dtype.str)
+        buf = self._pinned.get(key)
+        if buf is None:
+            buf = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+            self._pinned[key] = buf
+        buf.numpy()[...] = a
+        return buf.to(self.device, non_blocking=True).to(torch.float32)
+
+    def pinned_like(self, shape, dtype=np.float32):
+        """A pinned host tensor callers can fill in place and pass to siNet_get_reconstructed."""
+        return torch.empty(tuple(shape), dtype=torch.from_numpy(np.zeros(0, dtype)).dtype, pin_memory=True)
+
+    def _to_host(self, tensors):
+        self._ring ^= 1
+        outs = []
+        for i, t in enumerate(tensors):
+            key = ("out", i, self._ring, tuple(t.shape))
+            buf = self._pinned.get(key)
+            if buf is None:
+                buf = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+                self._pinned[key] = buf
+            buf.copy_(t, non_blocking=True)
+            outs.append(buf)
+        torch.cuda.current_stream().synchronize()
+        return [b.numpy() for b in outs]
+
+    # ------------------------------------------------------------------ inference
+    def reconstruct_device(self, x, y):
+        """Device-resident variant: x, y (B,3,H,W) fp32 CUDA tensors -> dict of CUDA tensors."""
+        B = x.shape[0]
+        both = torch.cat([y, x], dim=0)
+        z = self._encode(both, self.ae_imgcomp, is_training=False)
+        dec = self._decode(z.qbar, self.ae_imgcomp, is_training=False)
+        dec_nhwc = dec._dsin_nhwc
+        y_dec, x_dec = dec[:B], dec[B:]
+        y_dec._dsin_nhwc, x_dec._dsin_nhwc = dec_nhwc[:B], dec_nhwc[B:]
+        # bpp of x only (src/AE.py:85-87)
+        qx, sx = z.qbar[B:], z.symbols[B:]
+        bc = self.pc_imgcomp.bitcost(qx, sx, is_training=False,
+                                     pad_value=self.pc_imgcomp.auto_pad_value(self.ae_imgcomp))
+        out = {"y_dec": y_dec, "x_dec": x_dec, "symbols": sx, "bits": bc, "bits_sum": bc._dsin_sum}
+        if self.AE_only:
+            out["y_syn"] = torch.zeros_like(x)
+            out["x_with_si"] = torch.zeros_like(x)
+            return out
+        y_syn, _ncc, _arg, _q, _r, row, col, _xp, _yp = self._SI_full_img(
+            x_dec, y, self.mask, self._y_patch_h, self._y_patch_w, self.ae_config, y_dec)
+        fused = getattr(self._siNet, "fused", None)
+        if fused is not None and hasattr(y_syn, "_dsin_nhwc"):
+            x_with_si = fused(x_dec._dsin_nhwc, y_syn._dsin_nhwc)
+        else:  # generic callable: normalise/concat/denormalise with torch elementwise ops
+            mean, var = self.get_mean_var()
+            m = torch.from_numpy(mean).to(x.device)
+            s = torch.from_numpy(np.sqrt(var + 1e-10).astype(np.float32)).to(x.device)
+            cat = torch.cat([(x_dec - m) / s, (y_syn - m) / s], dim=1)
+            x_with_si = self._siNet(cat) * s + m
+        out.update({"y_syn": y_syn, "x_with_si": x_with_si, "row": row, "col": col,
+                    "best": getattr(y_syn, "_dsin_best", None)})
+        return out
+
+    def siNet_get_reconstructed(self, x, y):
+        """x, y: (B,3,H,W) arrays (uint8 or float32, uint8-valued).  Returns numpy
+        (y_dec, y_syn, x_dec, x_with_si, bpp) like src/AE.py:148.  The returned arrays are
+        views of pinned staging buffers that are recycled two calls later."""
+        xd, yd = self._to_device(x, "x"), self._to_device(y, "y")
+        out = self.reconstruct_device(xd, yd)
+        y_dec, y_syn, x_dec, x_with_si = self._to_host([out["y_dec"], out["y_syn"], out["x_dec"], out["x_with_si"]])
+        bpp = bits.bitcost_to_bpp(out["bits"], xd)
+        self.last = out
+        return y_dec, y_syn, x_dec, x_with_si, bpp
+
+    def create_y_dec(self, y):
+        yd = self._to_device(y, "y")
+        z = self._encode(yd, self.ae_imgcomp, is_training=False)
+        dec = self._decode(z.qbar, self.ae_imgcomp, is_training=False)
+        return self._to_host([dec])[0]

@@ -1,0 +1,143 @@
+"""Encoder/decoder networks (arch 'CVPR') on libdsin_b200 kernels.
+
+Mirrors the interface of /root/reference/src/autoencoder_imgcomp.py: ``get_network_cls``,
+``_Network.encode/decode/get_centers_variable``, ``EncoderOutput``; the bodies
+(:219-269, residual_block :275-288, BN scopes :106-125, heatmap :173-201, quantiser via
+quantizer_imgcomp.py:43-95) run as CUDA kernels on NHWC activations.  Inference only:
+BatchNorm is folded to a per-channel scale/shift at weight-load time.
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import ops, synth
+
+EncoderOutput = namedtuple("EncoderOutput", ["qbar", "qhard", "symbols", "z", "heatmap"])
+
+BN_EPS = np.float32(1e-5)
+arch_param_n = 128
+
+
+def get_network_cls(config):
+    return {"CVPR": _CVPR}[config.arch]
+
+
+def _fold_bn(W, scope):
+    g = W[scope + "/BatchNorm/gamma"].astype(np.float32)
+    b = W[scope + "/BatchNorm/beta"].astype(np.float32)
+    m = W[scope + "/BatchNorm/moving_mean"].astype(np.float32)
+    v = W[scope + "/BatchNorm/moving_variance"].astype(np.float32)
+    s = (g / np.sqrt(v + BN_EPS)).astype(np.float32)
+    return s, (b - m * s).astype(np.float32)
+
+
+class _Network(object):
+    def __init__(self, config, quantize=True):
+        self.config = config
+        self.quantize = quantize
+        self.num_chan_bn_including_heatmap = config.num_chan_bn + 1
+        self._centers = None
+        self.layers = {}
+        self.device = "cuda"
+
+    @staticmethod
+    def get_subsampling_factor():
+        raise NotImplementedError()
+
+    def get_centers_variable(self):
+        if self._centers is None:
+            raise ValueError("Call load_weights(...) before trying to access centers")
+        return self._centers
+
+    # -- weights ---------------------------------------------------------------------------
+    def _conv(self, W, scope, stride=1, relu=True, transposed=False, post=ops.POST_NONE):
+        w = W[scope + "/weights"]
+        if transposed:  # reference layout [k,k,out,in] -> [k,k,in,out]
+            w = np.transpose(w, (0, 1, 3, 2))
+        s, t = _fold_bn(W, scope)
+        self.layers[scope] = ops.ConvLayer(w, s, t, stride=stride, transposed=transposed,
+                                           act=ops.ACT_RELU if relu else ops.ACT_NONE, post=post,
+                                           device=self.device)
+
+    def load_weights(self, W):
+        raise NotImplementedError()
+
+    def encode(self, x, is_training=False):
+        if is_training is True:
+            raise NotImplementedError("dsin_b200 implements the inference path only")
+        return self._encode(x)
+
+    def decode(self, q, is_training=False):
+        if is_training is True:
+            raise NotImplementedError("dsin_b200 implements the inference path only")
+        return self._decode(q)
+
+
+class _CVPR(_Network):
+    @staticmethod
+    def get_subsampling_factor():
+        return 8
+
+    def load_weights(self, W):
+        B = self.config.arch_param_B
+        E, D = synth.ENC, synth.DEC
+        self._centers = torch.from_numpy(np.ascontiguousarray(W[E + "centers"], np.float32)).to(self.device)
+        self.centers_host = np.asarray(W[E + "centers"], np.float32).copy()
+        self._conv(W, E + "h1", stride=2)
+        self._conv(W, E + "h2", stride=2)
+        self._conv(W, E + "to_bn", stride=2, relu=False)
+        self._conv(W, D + "from_bn", stride=2, transposed=True)
+        self._conv(W, D + "h12", stride=2, transposed=True)
+        self._conv(W, D + "h13", stride=2, transposed=True, relu=False, post=ops.POST_DENORM_CLIP)
+        for pre, blk, fin in ((E, "res_block_enc_%d/enc_%d_%d", "res_block_enc_final"),
+                              (D, "res_block_dec_%d/dec_%d_%d", "dec_after_res")):
+            for b in range(B):
+                for i in (1, 2, 3):
+                    sc = pre + blk % (b, b, i)
+                    self._conv(W, sc + "/conv1", relu=True)
+                    self._conv(W, sc + "/conv2", relu=False)
+            self._conv(W, pre + fin + "/conv1", relu=False)  # activation_fn=None on both
+            self._conv(W, pre + fin + "/conv2", relu=False)
+
+    # -- trunk: 15 residual blocks + final block, 3 skip levels (shared by enc and dec) --------
+    def _trunk(self, net, pre, blk, fin):
+        L = self.layers
+        r0 = net
+        for b in range(self.config.arch_param_B):
+            rb = net
+            for i in (1, 2, 3):
+                sc = pre + blk % (b, b, i)
+                t = ops.conv2d(net, L[sc + "/conv1"])
+                # conv2 + BN, + block input, and (+ group input after the third block)
+                net = ops.conv2d(t, L[sc + "/conv2"], res1=net, res2=rb if i == 3 else None)
+        t = ops.conv2d(net, L[pre + fin + "/conv1"])
+        return ops.conv2d(t, L[pre + fin + "/conv2"], res1=net, res2=r0)
+
+    def _encode(self, x):
+        """x: (N,3,H,W) fp32 CUDA tensor, uint8-valued."""
+        L, E = self.layers, synth.ENC
+        net = ops.nchw_to_nhwc(x, normalize=True)
+        net = ops.conv2d(net, L[E + "h1"])
+        net = ops.conv2d(net, L[E + "h2"])
+        net = self._trunk(net, E, "res_block_enc_%d/enc_%d_%d", "res_block_enc_final")
+        z33 = ops.conv2d(net, L[E + "to_bn"])
+        qbar_nhwc, qbar_nchw, symbols = ops.heatmap_quantize(z33, self._centers)
+        qbar_nchw._dsin_nhwc = qbar_nhwc
+        return EncoderOutput(qbar_nchw, None, symbols, None, None)
+
+    def _decode(self, q):
+        """q: qbar (N,C,h,w); returns x_dec (N,3,H,W) clipped to [0,255]."""
+        L, D = self.layers, synth.DEC
+        q_nhwc = getattr(q, "_dsin_nhwc", None)
+        if q_nhwc is None:
+            q_nhwc = ops.nchw_to_nhwc(q.contiguous(), normalize=False)
+        net = ops.conv2d(q_nhwc, L[D + "from_bn"])
+        net = self._trunk(net, D, "res_block_dec_%d/dec_%d_%d", "dec_after_res")
+        net = ops.conv2d(net, L[D + "h12"])
+        img_nhwc = ops.conv2d(net, L[D + "h13"])  # BN, denormalise, clip fused
+        out = ops.nhwc_to_nchw(img_nhwc)
+        out._dsin_nhwc = img_nhwc
+        return out

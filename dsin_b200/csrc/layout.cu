@@ -1,0 +1,103 @@
+// Layout conversion + normalisation kernels (HBM-bound, trivially small).
+#include "common.cuh"
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int c,
+                                    int hw, int normalize) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*hw pixels
+  if (idx >= (int64_t)n * hw) return;
+  int img = (int)(idx / hw);
+  int pix = (int)(idx % hw);
+  for (int ch = 0; ch < c; ++ch) {
+    float v = x[((int64_t)img * c + ch) * hw + pix];  // coalesced over pix
+    if (normalize) v = __fdiv_rn(__fsub_rn(v, dsin_mean(ch)), dsin_std(ch));
+    y[idx * c + ch] = v;
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int c,
+                                    int hw) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n * hw) return;
+  int img = (int)(idx / hw);
+  int pix = (int)(idx % hw);
+  for (int ch = 0; ch < c; ++ch) y[((int64_t)img * c + ch) * hw + pix] = x[idx * c + ch];
+}
+
+__global__ void concat_normalize_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                        float* __restrict__ out, int64_t npix) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npix) return;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    out[idx * 6 + ch] = __fdiv_rn(__fsub_rn(a[idx * 3 + ch], dsin_mean(ch)), dsin_std(ch));
+    out[idx * 6 + 3 + ch] = __fdiv_rn(__fsub_rn(b[idx * 3 + ch], dsin_mean(ch)), dsin_std(ch));
+  }
+}
+
+__global__ void f32_to_split_kernel(const float* __restrict__ x, __half* __restrict__ hi,
+                                    __half* __restrict__ lo, int64_t count) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float v = x[i];
+  __half h = __float2half_rn(v);
+  hi[i] = h;
+  lo[i] = __float2half_rn(v - __half2float(h));
+}
+
+__global__ void split_to_f32_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                    float* __restrict__ y, int64_t count) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  y[i] = __half2float(hi[i]) + __half2float(lo[i]);
+}
+
+extern "C" {
+
+int dsin_nchw_to_nhwc(dsin_handle_t h, const float* x, float* y, int n, int c, int hh, int ww,
+                      int normalize, void* stream) {
+  DSIN_REQUIRE(h, x && y && n > 0 && c > 0 && hh > 0 && ww > 0, "bad argument");
+  DSIN_REQUIRE(h, !normalize || c == 3, "normalisation needs 3 channels");
+  int64_t tot = (int64_t)n * hh * ww;
+  nchw_to_nhwc_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, c, hh * ww,
+                                                                                   normalize);
+  DSIN_LAUNCHED(h);
+  return DSIN_OK;
+}
+
+int dsin_nhwc_to_nchw(dsin_handle_t h, const float* x, float* y, int n, int c, int hh, int ww,
+                      void* stream) {
+  DSIN_REQUIRE(h, x && y && n > 0 && c > 0 && hh > 0 && ww > 0, "bad argument");
+  int64_t tot = (int64_t)n * hh * ww;
+  nhwc_to_nchw_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, c, hh * ww);
+  DSIN_LAUNCHED(h);
+  return DSIN_OK;
+}
+
+int dsin_concat_normalize(dsin_handle_t h, const float* a, const float* b, float* out, int n, int hh,
+                          int ww, void* stream) {
+  DSIN_REQUIRE(h, a && b && out && n > 0, "bad argument");
+  int64_t tot = (int64_t)n * hh * ww;
+  concat_normalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, tot);
+  DSIN_LAUNCHED(h);
+  return DSIN_OK;
+}
+
+int dsin_f32_to_split(dsin_handle_t h, const float* x, uint16_t* hi, uint16_t* lo, int64_t count,
+                      void* stream) {
+  DSIN_REQUIRE(h, x && hi && lo && count > 0, "bad argument");
+  f32_to_split_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, (__half*)hi, (__half*)lo, count);
+  DSIN_LAUNCHED(h);
+  return DSIN_OK;
+}
+
+int dsin_split_to_f32(dsin_handle_t h, const uint16_t* hi, const uint16_t* lo, float* y, int64_t count,
+                      void* stream) {
+  DSIN_REQUIRE(h, y && hi && lo && count > 0, "bad argument");
+  split_to_f32_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)hi, (const __half*)lo, y, count);
+  DSIN_LAUNCHED(h);
+  return DSIN_OK;
+}
+
+}  // extern "C"

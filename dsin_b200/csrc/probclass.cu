@@ -1,0 +1,209 @@
+// K4: 3-D masked-conv probability model -> per-symbol bits and per-image bit sums.
+// src/probclass_imgcomp.py:63-106 (bitcost), :150-176 (masks), :185-196 (residual), :214-221
+// (_ResShallow._logits), :258-260 (conv3d + bias + activation), :268-292 (padding).
+// Volume axes: D = bottleneck channel, H, W; activations are channels-last (N,D,H,W,K).
+// v1: one direct-conv kernel per layer (CUDA cores), weights staged in shared memory,
+// dead (masked) taps skipped; layer 0 reads qbar with the centres[0] padding applied on the fly;
+// the last layer fuses ReLU + log-sum-exp cross entropy + log2(e) and the per-image fp64 sum.
+#include "common.cuh"
+
+struct PcP {
+  const float* in;     // layer input (N,Di,Hi,Wi,CIN) or qbar_nchw for the first layer
+  const float* w;      // [2][3][3][CIN][COUT]
+  const float* b;      // [COUT]
+  const float* skip;   // residual source (N,Ds,Hs,Ws,COUT) or null (cropped [2:,2:-2,2:-2])
+  float* out;          // (N,Do,Ho,Wo,COUT) or null
+  const int64_t* sym;  // last layer only
+  float* bits;         // last layer only, may be null (N,C,H,W)
+  double* bits_sum;    // last layer only (N)
+  int n, Di, Hi, Wi;   // input volume dims (for the first layer: padded dims)
+  int c, hh, ww;       // bottleneck dims (first layer addressing)
+  float pad_value;
+  unsigned live_mask;  // bit t set = tap t (d*9+h*3+w) has non-zero mask
+  int relu;
+};
+
+template <int CIN, int COUT, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(128) pc_conv3d_kernel(PcP p) {
+  extern __shared__ float s_w[];  // [18][CIN][COUT] + bias[COUT]
+  float* s_b = s_w + 18 * CIN * COUT;
+  for (int i = threadIdx.x; i < 18 * CIN * COUT; i += blockDim.x) s_w[i] = p.w[i];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_b[i] = p.b[i];
+  __syncthreads();
+
+  const int Do = p.Di - 1, Ho = p.Hi - 2, Wo = p.Wi - 2;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)p.n * Do * Ho * Wo;
+  bool active = idx < total;
+  int wq = 0, hq = 0, dq = 0, img = 0;
+  if (active) {
+    wq = (int)(idx % Wo);
+    int64_t t = idx / Wo;
+    hq = (int)(t % Ho);
+    t /= Ho;
+    dq = (int)(t % Do);
+    img = (int)(t / Do);
+  }
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+  if (active) {
+#pragma unroll
+    for (int t = 0; t < 18; ++t) {
+      if (!((p.live_mask >> t) & 1u)) continue;
+      int dd = t / 9, dh = (t / 3) % 3, dw = t % 3;
+      int id = dq + dd, ih = hq + dh, iw = wq + dw;
+      if (FIRST) {
+        // padded volume (C+4, H+8, W+8), value = qbar or pad_value
+        int cc = id - 4, yy = ih - 4, xx = iw - 4;
+        float v = p.pad_value;
+        if (cc >= 0 && yy >= 0 && yy < p.hh && xx >= 0 && xx < p.ww)
+          v = __ldg(p.in + (((int64_t)img * p.c + cc) * p.hh + yy) * p.ww + xx);
+        const float* wt = s_w + t * COUT;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] = fmaf(v, wt[o], acc[o]);
+      } else {
+        const float* ip = p.in + ((((int64_t)img * p.Di + id) * p.Hi + ih) * p.Wi + iw) * CIN;
+        const float* wt = s_w + t * CIN * COUT;
+#pragma unroll 4
+        for (int ci = 0; ci < CIN; ++ci) {
+          float v = __ldg(ip + ci);
+#pragma unroll
+          for (int o = 0; o < COUT; ++o) acc[o] = fmaf(v, wt[ci * COUT + o], acc[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+      float v = __fadd_rn(acc[o], s_b[o]);
+      if (p.relu) v = fmaxf(v, 0.f);
+      acc[o] = v;
+    }
+    if (p.skip) {
+      // residual_input[..., 2:, 2:-2, 2:-2, :] -- skip volume is (Do+2, Ho+4, Wo+4)
+      const float* sp = p.skip + ((((int64_t)img * (Do + 2) + dq + 2) * (Ho + 4) + hq + 2) * (Wo + 4) + wq + 2) * COUT;
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) acc[o] = __fadd_rn(acc[o], sp[o]);
+    }
+  }
+  if (!LAST) {
+    if (active) {
+      float* op = p.out + idx * COUT;
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) op[o] = acc[o];
+    }
+  } else {
+    // softmax cross entropy with the target symbol, in bits
+    double mybits = 0.0;
+    if (active) {
+      float m = acc[0];
+#pragma unroll
+      for (int o = 1; o < COUT; ++o) m = fmaxf(m, acc[o]);
+      float s = 0.f;
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) s = __fadd_rn(s, expf(__fsub_rn(acc[o], m)));
+      float lse = __fadd_rn(m, logf(s));
+      int64_t o_nchw = (((int64_t)img * Do + dq) * Ho + hq) * Wo + wq;
+      int sy = (int)p.sym[o_nchw];
+      float picked = 0.f;
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) picked = (o == sy) ? acc[o] : picked;
+      float bit = __fmul_rn(__fsub_rn(lse, picked), 1.4426950408889634f);
+      if (p.bits) p.bits[o_nchw] = bit;
+      mybits = (double)bit;
+    }
+    // block reduction; a block never straddles images when Do*Ho*Wo % blockDim != 0 -> handle generally
+    __shared__ double s_red[128];
+    __shared__ int s_img[128];
+    s_red[threadIdx.x] = mybits;
+    s_img[threadIdx.x] = active ? img : -1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int cur = -1;
+      double sum = 0.0;
+      for (int i = 0; i < (int)blockDim.x; ++i) {
+        if (s_img[i] < 0) continue;
+        if (s_img[i] != cur) {
+          if (cur >= 0) atomicAdd(p.bits_sum + cur, sum);
+          cur = s_img[i];
+          sum = 0.0;
+        }
+        sum += s_red[i];
+      }
+      if (cur >= 0) atomicAdd(p.bits_sum + cur, sum);
+    }
+  }
+}
+
+static unsigned pc_live_mask(bool first) {
+  // tap index t = d*9 + h*3 + w ; depth slice d=1 is the "current" slice
+  unsigned m = 0;
+  for (int d = 0; d < 2; ++d)
+    for (int hh = 0; hh < 3; ++hh)
+      for (int ww = 0; ww < 3; ++ww) {
+        bool live = true;
+        if (d == 1) {
+          if (hh > 1) live = false;
+          if (hh == 1 && (first ? ww >= 1 : ww > 1)) live = false;
+        }
+        if (live) m |= 1u << (d * 9 + hh * 3 + ww);
+      }
+  return m;
+}
+
+extern "C" int64_t dsin_probclass_workspace_bytes(int n, int c, int hh, int ww, int k) {
+  int64_t v0 = (int64_t)(c + 3) * (hh + 6) * (ww + 6);
+  int64_t v1 = (int64_t)(c + 2) * (hh + 4) * (ww + 4);
+  int64_t v2 = (int64_t)(c + 1) * (hh + 2) * (ww + 2);
+  return (v0 + v1 + v2) * n * k * (int64_t)sizeof(float) + 1024;
+}
+
+extern "C" int dsin_probclass_bits(dsin_handle_t h, const float* qbar, const int64_t* symbols, int n, int c,
+                                   int hh, int ww, int k, int L, float pad_value, const float* w0,
+                                   const float* b0, const float* w1, const float* b1, const float* w2,
+                                   const float* b2, const float* w3, const float* b3, float* bits_nchw,
+                                   double* bits_sum, void* workspace, void* stream) {
+  DSIN_REQUIRE(h, qbar && symbols && bits_sum && workspace, "null pointer");
+  DSIN_REQUIRE(h, k == 24 && L == 6, "only arch res_shallow with k=24, L=6 is built");
+  DSIN_REQUIRE(h, w0 && b0 && w1 && b1 && w2 && b2 && w3 && b3, "null weights");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t v0 = (int64_t)n * (c + 3) * (hh + 6) * (ww + 6);
+  int64_t v1 = (int64_t)n * (c + 2) * (hh + 4) * (ww + 4);
+  int64_t v2 = (int64_t)n * (c + 1) * (hh + 2) * (ww + 2);
+  float* a0 = (float*)workspace;
+  float* a1 = a0 + v0 * k;
+  float* a2 = a1 + v1 * k;
+  if (cudaMemsetAsync(bits_sum, 0, sizeof(double) * n, st) != cudaSuccess)
+    return dsin_fail(h, DSIN_ERR_CUDA, "%s: memset failed", __func__);
+  const unsigned first = pc_live_mask(true), other = pc_live_mask(false);
+  PcP p;
+  memset(&p, 0, sizeof(p));
+  p.n = n; p.c = c; p.hh = hh; p.ww = ww; p.pad_value = pad_value;
+  // layer 0: padded (c+4, hh+8, ww+8, 1) -> (c+3, hh+6, ww+6, 24), ReLU
+  p.in = qbar; p.w = w0; p.b = b0; p.skip = nullptr; p.out = a0; p.Di = c + 4; p.Hi = hh + 8; p.Wi = ww + 8;
+  p.live_mask = first; p.relu = 1;
+  {
+    size_t smem = (18 * 1 * 24 + 24) * sizeof(float);
+    pc_conv3d_kernel<1, 24, true, false><<<(unsigned)((v0 + 127) / 128), 128, smem, st>>>(p);
+    DSIN_LAUNCHED(h);
+  }
+  size_t smem24 = (18 * 24 * 24 + 24) * sizeof(float);
+  // res1/conv1: ReLU
+  p.in = a0; p.w = w1; p.b = b1; p.out = a1; p.Di = c + 3; p.Hi = hh + 6; p.Wi = ww + 6; p.live_mask = other;
+  pc_conv3d_kernel<24, 24, false, false><<<(unsigned)((v1 + 127) / 128), 128, smem24, st>>>(p);
+  DSIN_LAUNCHED(h);
+  // res1/conv2: no activation, + cropped skip from a0
+  p.in = a1; p.w = w2; p.b = b2; p.out = a2; p.skip = a0; p.Di = c + 2; p.Hi = hh + 4; p.Wi = ww + 4; p.relu = 0;
+  pc_conv3d_kernel<24, 24, false, false><<<(unsigned)((v2 + 127) / 128), 128, smem24, st>>>(p);
+  DSIN_LAUNCHED(h);
+  // conv2: 24 -> 6, ReLU, fused cross entropy
+  p.in = a2; p.w = w3; p.b = b3; p.out = nullptr; p.skip = nullptr; p.Di = c + 1; p.Hi = hh + 2; p.Wi = ww + 2;
+  p.relu = 1; p.sym = symbols; p.bits = bits_nchw; p.bits_sum = bits_sum;
+  {
+    int64_t v3 = (int64_t)n * c * hh * ww;
+    size_t smem = (18 * 24 * 6 + 6) * sizeof(float);
+    pc_conv3d_kernel<24, 6, false, true><<<(unsigned)((v3 + 127) / 128), 128, smem, st>>>(p);
+    DSIN_LAUNCHED(h);
+  }
+  return DSIN_OK;
+}

@@ -1,0 +1,173 @@
+"""Thin torch-tensor wrappers over the C ABI (include/dsin_b200.h).
+
+torch is used for device memory and streams only; every arithmetic op below is a kernel of
+libdsin_b200.so launched on torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT_LRELU02, ACT_NONE, ACT_RELU, POST_DENORM, POST_DENORM_CLIP, POST_NONE, ConvDesc  # noqa: F401
+
+_handles = {}
+
+
+def handle(device=None):
+    if not torch.cuda.is_available():
+        raise _lib.DsinLibraryError("CUDA device required: dsin_b200 has no CPU fallback")
+    dev = torch.cuda.current_device() if device is None else int(device)
+    if dev not in _handles:
+        _handles[dev] = _lib.Handle(dev)
+    return _handles[dev]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _chk(t, dtype=torch.float32):
+    assert t.is_cuda and t.is_contiguous() and t.dtype == dtype, (t.device, t.is_contiguous(), t.dtype)
+    return t
+
+
+def launch_count():
+    return sum(h.launch_count() for h in _handles.values())
+
+
+def nchw_to_nhwc(x, normalize=False):
+    h = handle()
+    n, c, hh, ww = x.shape
+    y = torch.empty((n, hh, ww, c), dtype=torch.float32, device=x.device)
+    h.check(h.lib.dsin_nchw_to_nhwc(h.ptr, _p(_chk(x)), _p(y), n, c, hh, ww, int(normalize), _stream()))
+    return y
+
+
+def nhwc_to_nchw(x):
+    h = handle()
+    n, hh, ww, c = x.shape
+    y = torch.empty((n, c, hh, ww), dtype=torch.float32, device=x.device)
+    h.check(h.lib.dsin_nhwc_to_nchw(h.ptr, _p(_chk(x)), _p(y), n, c, hh, ww, _stream()))
+    return y
+
+
+def concat_normalize(xdec_nhwc, ysyn_nhwc):
+    h = handle()
+    n, hh, ww, _ = xdec_nhwc.shape
+    out = torch.empty((n, hh, ww, 6), dtype=torch.float32, device=xdec_nhwc.device)
+    h.check(h.lib.dsin_concat_normalize(h.ptr, _p(_chk(xdec_nhwc)), _p(_chk(ysyn_nhwc)), _p(out), n, hh, ww,
+                                        _stream()))
+    return out
+
+
+class ConvLayer(object):
+    """Device-resident packed parameters of one conv (+ folded BN or bias)."""
+
+    def __init__(self, w_kkio, scale, shift, stride=1, dilation=1, transposed=False, act=ACT_NONE,
+                 post=POST_NONE, device="cuda"):
+        w = np.ascontiguousarray(w_kkio, dtype=np.float32)
+        self.kh, self.kw, self.cin, self.cout = w.shape
+        self.w = torch.from_numpy(w).to(device)
+        self.scale = None if scale is None else torch.from_numpy(np.ascontiguousarray(scale, np.float32)).to(device)
+        self.shift = None if shift is None else torch.from_numpy(np.ascontiguousarray(shift, np.float32)).to(device)
+        self.stride, self.dilation, self.transposed, self.act, self.post = stride, dilation, transposed, act, post
+
+    def out_hw(self, hh, ww):
+        if self.transposed:
+            return 2 * hh, 2 * ww
+        return -(-hh // self.stride), -(-ww // self.stride)
+
+
+def conv2d(x, layer, res1=None, res2=None, scale=None, shift=None, act=None, post=None):
+    """y = post(act(conv(x)*scale + shift) + res1 + res2), NHWC fp32."""
+    h = handle()
+    n, hh, ww, cin = x.shape
+    assert cin == layer.cin, (cin, layer.cin)
+    oh, ow = layer.out_hw(hh, ww)
+    y = torch.empty((n, oh, ow, layer.cout), dtype=torch.float32, device=x.device)
+    d = ConvDesc(n, hh, ww, cin, layer.cout, layer.kh, layer.kw, layer.stride, layer.dilation,
+                 int(layer.transposed), layer.act if act is None else act, layer.post if post is None else post)
+    sc = layer.scale if scale is None else scale
+    sh = layer.shift if shift is None else shift
+    if res1 is not None:
+        assert res1.shape == y.shape
+    if res2 is not None:
+        assert res2.shape == y.shape
+    h.check(h.lib.dsin_conv2d(h.ptr, C.byref(d), _p(_chk(x)), _p(layer.w), _p(sc), _p(sh), _p(res1), _p(res2),
+                              _p(y), _stream()))
+    return y
+
+
+def heatmap_quantize(z33_nhwc, centers):
+    h = handle()
+    n, hh, ww, c1 = z33_nhwc.shape
+    c = c1 - 1
+    dev = z33_nhwc.device
+    qbar_nhwc = torch.empty((n, hh, ww, c), dtype=torch.float32, device=dev)
+    qbar_nchw = torch.empty((n, c, hh, ww), dtype=torch.float32, device=dev)
+    sym = torch.empty((n, c, hh, ww), dtype=torch.int64, device=dev)
+    h.check(h.lib.dsin_heatmap_quantize(h.ptr, _p(_chk(z33_nhwc)), _p(_chk(centers)), centers.numel(), n, hh, ww, c,
+                                        _p(qbar_nhwc), _p(qbar_nchw), _p(sym), _stream()))
+    return qbar_nhwc, qbar_nchw, sym
+
+
+def probclass_bits(qbar_nchw, symbols, weights, pad_value, k=24, L=6, want_bits=True):
+    """weights: list of 4 (w, b) device tensors, mask applied, layout [2][3][3][cin][cout]."""
+    h = handle()
+    n, c, hh, ww = qbar_nchw.shape
+    dev = qbar_nchw.device
+    ws = int(h.lib.dsin_probclass_workspace_bytes(n, c, hh, ww, k))
+    work = torch.empty(ws, dtype=torch.uint8, device=dev)
+    bits = torch.empty((n, c, hh, ww), dtype=torch.float32, device=dev) if want_bits else None
+    sums = torch.empty((n,), dtype=torch.float64, device=dev)
+    flat = []
+    for w, b in weights:
+        flat += [_p(_chk(w)), _p(_chk(b))]
+    h.check(h.lib.dsin_probclass_bits(h.ptr, _p(_chk(qbar_nchw)), _p(_chk(symbols, torch.int64)), n, c, hh, ww, k, L,
+                                      C.c_float(float(pad_value)), *flat, _p(bits), _p(sums), _p(work), _stream()))
+    return bits, sums
+
+
+def sif_prepare(xdec_nhwc, ydec_nhwc, ph, pw):
+    h = handle()
+    n, hh, ww, _ = xdec_nhwc.shape
+    dev = xdec_nhwc.device
+    P = (hh // ph) * (ww // pw)
+    q = torch.empty((n, P, ph * pw * 3), dtype=torch.float32, device=dev)
+    r = torch.empty((n, hh, ww, 3), dtype=torch.float32, device=dev)
+    pstat = torch.empty((n, P, 4), dtype=torch.float32, device=dev)
+    ystat = torch.empty((n, hh - ph + 1, ww - pw + 1, 4), dtype=torch.float32, device=dev)
+    h.check(h.lib.dsin_sif_prepare(h.ptr, _p(_chk(xdec_nhwc)), _p(_chk(ydec_nhwc)), n, hh, ww, ph, pw, _p(q), _p(r),
+                                   _p(pstat), _p(ystat), _stream()))
+    return q, r, pstat, ystat
+
+
+def sif_match(q, r, pstat, ystat, ph, pw, use_mask=True, method=0):
+    h = handle()
+    n, hh, ww, _ = r.shape
+    P = q.shape[1]
+    dev = r.device
+    ws = int(h.lib.dsin_sif_workspace_bytes(n, hh, ww, ph, pw, method))
+    work = torch.empty(ws, dtype=torch.uint8, device=dev)
+    row = torch.empty((n, P), dtype=torch.int32, device=dev)
+    col = torch.empty((n, P), dtype=torch.int32, device=dev)
+    best = torch.empty((n, P), dtype=torch.float32, device=dev)
+    h.check(h.lib.dsin_sif_match(h.ptr, _p(_chk(q)), _p(_chk(r)), _p(_chk(pstat)), _p(_chk(ystat)), n, hh, ww, ph, pw,
+                                 int(use_mask), int(method), _p(row), _p(col), _p(best), _p(work), _stream()))
+    return row, col, best
+
+
+def sif_gather(y_nhwc, row, col, ph, pw):
+    h = handle()
+    n, hh, ww, _ = y_nhwc.shape
+    out = torch.empty_like(y_nhwc)
+    h.check(h.lib.dsin_sif_gather(h.ptr, _p(_chk(y_nhwc)), _p(_chk(row, torch.int32)), _p(_chk(col, torch.int32)), n,
+                                  hh, ww, ph, pw, _p(out), _stream()))
+    return out

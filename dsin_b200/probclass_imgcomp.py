@@ -1,0 +1,76 @@
+"""3-D masked-conv probability model (arch 'res_shallow') on libdsin_b200.
+
+Mirrors /root/reference/src/probclass_imgcomp.py: ``get_network_cls``, ``_Network3D.bitcost``
+(:63-106), ``auto_pad_value`` (:59-61), masks (:150-176).  The arithmetic-coding helpers
+(:361-482) are unused by the reference's main.py and are out of scope.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops, synth
+
+
+def get_network_cls(pc_config):
+    return {"res_shallow": _ResShallow}[pc_config.arch]
+
+
+def create_masks(K=3):
+    """first_mask / other_mask, DHW (src/probclass_imgcomp.py:150-176)."""
+    first = np.ones((K // 2 + 1, K, K), dtype=np.float32)
+    first[-1, K // 2, K // 2:] = 0
+    first[-1, K // 2 + 1:, :] = 0
+    other = np.ones((K // 2 + 1, K, K), dtype=np.float32)
+    other[-1, K // 2, K // 2 + 1:] = 0
+    other[-1, K // 2 + 1:, :] = 0
+    return first, other
+
+
+class _ResShallow(object):
+    _PROBCLASS_SCOPE = "probclass3d"
+
+    def __init__(self, pc_config, num_centers):
+        self.config = pc_config
+        self.L = num_centers
+        if pc_config.kernel_size != 3:
+            raise ValueError("only kernel_size 3 is built")
+        self.first_mask, self.other_mask = create_masks(pc_config.kernel_size)
+        self.weights = None
+        self.device = "cuda"
+
+    @classmethod
+    def get_num_layers(cls):
+        return 4
+
+    @classmethod
+    def get_context_size(cls, config):
+        return cls.get_num_layers() * (config.kernel_size - 1) + 1
+
+    def auto_pad_value(self, ae):
+        if not self.config.use_centers_for_padding:
+            return 0.0
+        return float(ae.centers_host[0])
+
+    def load_weights(self, W):
+        P = synth.PC
+        out = []
+        for name, mask in (("conv3d_conv0_mask", self.first_mask), ("res1/conv3d_conv1_mask", self.other_mask),
+                           ("res1/conv3d_conv2_mask", self.other_mask), ("conv3d_conv2_mask", self.other_mask)):
+            w = W[P + name + "/weights"].astype(np.float32) * mask[..., None, None]
+            b = W[P + name + "/biases"].astype(np.float32)
+            out.append((torch.from_numpy(np.ascontiguousarray(w)).to(self.device),
+                        torch.from_numpy(np.ascontiguousarray(b)).to(self.device)))
+        self.weights = out
+
+    def bitcost(self, q, target_symbols, is_training=False, pad_value=0):
+        """q: qbar NCHW fp32, target_symbols NCHW int64 -> bits per symbol NCHW.  The fp64
+        per-image sums ride along as ``._dsin_sum`` for bits_imgcomp.bitcost_to_bpp."""
+        if is_training is True:
+            raise NotImplementedError("dsin_b200 implements the inference path only")
+        if q.dim() != 4:
+            raise ValueError("expected NCHW, got {}".format(tuple(q.shape)))
+        bits, sums = ops.probclass_bits(q.contiguous(), target_symbols.contiguous(), self.weights,
+                                        float(pad_value), k=self.config.arch_param__k, L=self.L)
+        bits._dsin_sum = sums
+        return bits

@@ -1,0 +1,58 @@
+"""Helpers shared by the GPU parity tests: calibrated synthetic weights, the AE factory, and
+near-tie adjudication against the float64 oracle."""
+import os
+
+import numpy as np
+import torch
+
+from dsin_b200 import config_parser, synth
+from oracle import dsin_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = os.path.join(ROOT, "dsin_b200", "run_configs")
+
+_WCACHE = {}
+
+
+def calibrated_weights(seed=0):
+    if seed not in _WCACHE:
+        W = synth.make_weights(seed)
+        x, y = synth.make_batch(2, 80, 144, seed=4242 + seed)
+        O.calibrate_bn(W, np.concatenate([x, y]))
+        _WCACHE[seed] = W
+    return _WCACHE[seed]
+
+
+def configs(H, W):
+    ae_config, _ = config_parser.parse(os.path.join(CFG, "ae_run_configs"))
+    pc_config, _ = config_parser.parse(os.path.join(CFG, "pc_run_configs"))
+    ae_config.crop_size = (H, W)
+    return ae_config, pc_config
+
+
+def make_ae(H, W, weights):
+    from dsin_b200.AE import AE
+    from dsin_b200.decoder_imgcomp import decoder
+    from dsin_b200.encoder_imgcomp import encoder
+    from dsin_b200.siFinder import siFinder
+    from dsin_b200.siFull_img import SI_full_img
+    from dsin_b200.siNet import siNet
+    ae_config, pc_config = configs(H, W)
+    return AE(ae_config, pc_config, encoder, decoder, siFinder, SI_full_img, siNet, CFG, weights=weights)
+
+
+def symbol_report(sym_gpu, x_np, W, margin_tol=2e-4):
+    """Compare GPU symbols with the fp32 oracle; every mismatch must be a near-tie according to
+    the float64 oracle (the two nearest centres are within margin_tol of equidistant)."""
+    enc32 = O.encode(torch.as_tensor(x_np, dtype=torch.float32), W)
+    mism = (sym_gpu != enc32.symbols)
+    n_mism = int(mism.sum())
+    bad = 0
+    if n_mism:
+        enc64 = O.encode(torch.as_tensor(x_np, dtype=torch.float64), W)
+        c = torch.as_tensor(W[O.ENC + "centers"], dtype=torch.float64)
+        d = (enc64.z.unsqueeze(-1) - c).abs()
+        ds, _ = torch.sort(d, dim=-1)
+        margin = (ds[..., 1] - ds[..., 0])[mism]
+        bad = int((margin > margin_tol).sum())
+    return n_mism, bad, int(sym_gpu.numel())

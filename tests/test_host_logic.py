@@ -1,0 +1,74 @@
+"""Host-side logic that runs without a GPU: config parser, synthetic generators, weight naming."""
+import os
+
+import numpy as np
+import pytest
+
+from dsin_b200 import config_parser, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_parse_shipped_configs():
+    ae, rel = config_parser.parse(os.path.join(ROOT, "dsin_b200", "run_configs", "ae_run_configs"))
+    pc, _ = config_parser.parse(os.path.join(ROOT, "dsin_b200", "run_configs", "pc_run_configs"))
+    assert rel == "ae_run_configs"
+    assert ae.crop_size == (320, 1224) and ae.y_patch_size == (20, 24) and ae.batch_size == 1
+    assert ae.H_target == pytest.approx(0.04) and ae.normalization == "FIXED" and ae.distortion_to_minimize == "mae"
+    assert ae.arch == "CVPR" and ae.arch_param_B == 5 and ae.num_chan_bn == 32 and ae.num_centers == 6
+    assert ae.AE_only is False and ae.use_gauss_mask is True and ae.lr_centers_factor is None
+    assert pc.arch == "res_shallow" and pc.kernel_size == 3 and pc.arch_param__k == 24
+    assert pc.use_centers_for_padding is True and pc.regularization_factor is None
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/run_configs/ae_run_configs"), reason="reference absent")
+def test_parse_reference_config_files_verbatim():
+    ae, _ = config_parser.parse("/root/reference/src/run_configs/ae_run_configs")
+    mine, _ = config_parser.parse(os.path.join(ROOT, "dsin_b200", "run_configs", "ae_run_configs"))
+    assert dict(ae.all_params_and_values()) == dict(mine.all_params_and_values())
+    pc, _ = config_parser.parse("/root/reference/src/run_configs/pc_run_configs")
+    minepc, _ = config_parser.parse(os.path.join(ROOT, "dsin_b200", "run_configs", "pc_run_configs"))
+    assert dict(pc.all_params_and_values()) == dict(minepc.all_params_and_values())
+
+
+def test_constraint_violation_and_bad_lines():
+    with pytest.raises(ValueError):
+        config_parser.parse_string("constrain opt :: A, B\nopt = C\n")
+    with pytest.raises(ValueError):
+        config_parser.parse_string("this is not a config line\n")
+    cfg = config_parser.parse_string("a = 2*3  # trailing\nb = (a, 'x#y')\n")
+    assert cfg.a == 6 and cfg.b == (6, "x#y")
+
+
+def test_weight_names_and_shapes():
+    W = synth.make_weights(0)
+    assert W[synth.ENC + "h1/weights"].shape == (5, 5, 3, 64)
+    assert W[synth.ENC + "to_bn/weights"].shape == (5, 5, 128, 33)
+    assert W[synth.ENC + "res_block_enc_4/enc_4_3/conv2/weights"].shape == (3, 3, 128, 128)
+    assert W[synth.DEC + "from_bn/weights"].shape == (3, 3, 128, 32)
+    assert W[synth.DEC + "h13/weights"].shape == (5, 5, 3, 64)
+    assert W[synth.PC + "res1/conv3d_conv1_mask/weights"].shape == (2, 3, 3, 24, 24)
+    assert W[synth.SIN + "g_conv1/weights"].shape == (3, 3, 6, 32)
+    assert W[synth.SIN + "g_conv_last/weights"].shape == (1, 1, 32, 3)
+    n_ae = sum(v.size for k, v in W.items() if k.endswith("/weights") and ("encoder" in k or k.startswith("decoder")))
+    assert 9.9e6 < n_ae < 10.2e6  # ~10.0 M conv parameters
+    assert len(synth.enc_conv_scopes()) == 34 and len(synth.dec_conv_scopes()) == 32
+
+
+def test_weights_roundtrip(tmp_path):
+    W = synth.make_weights(1)
+    p = str(tmp_path / "w.npz")
+    synth.save_weights(p, W)
+    W2 = synth.load_weights(p)
+    assert sorted(W) == sorted(W2)
+    assert all(np.array_equal(W[k], W2[k]) for k in W)
+
+
+def test_synthetic_pairs_are_seeded_and_uint8_valued():
+    x1, y1 = synth.make_pair(5, 80, 144)
+    x2, y2 = synth.make_pair(5, 80, 144)
+    assert np.array_equal(x1, x2) and np.array_equal(y1, y2)
+    assert x1.shape == (3, 80, 144) and x1.dtype == np.float32
+    assert np.array_equal(x1, np.floor(x1)) and x1.min() >= 0 and x1.max() <= 255
+    xs, ys = synth.make_batch(3, 40, 48, seed=9)
+    assert xs.shape == (3, 3, 40, 48) and ys.shape == xs.shape
