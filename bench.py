@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- DSIN inference hot path on B200 (one JSON line on stdout, rank 0).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (libdsin_b200)
+  python bench.py --impl reference ...                      the reference arithmetic on host cores
+
+A "step" is one AE.siNet_get_reconstructed-equivalent pass (AE(y), AE(x), bpp, SI-Finder, SI-Net;
+/root/reference/src/AE.py:132-148) over one batch of synthetic 320x1224 pairs.  N=1 workload =
+BASELINE.json configs[1] (batch 8, full inference).  `value` = Mpixels/s with inputs resident in
+HBM; `e2e` = the same through the public numpy call with pinned host buffers (H2D + D2H inside the
+timed region).  N>1: one process per GPU (torchrun), pairs sharded, one NCCL all-gather of per-rank
+metric partials; timing is the max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 320, 1224
+PH, PW = 20, 24
+GFLOP_PER_PAIR_FULL = 1893.9  # SURVEY App. B / BASELINE.md section 4
+METRIC = "Mpixels/s decode (320x1224 pairs)"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p["bf16_tflops_sustained"], src="measured")
+    except Exception:  # noqa: BLE001
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nme, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:  # noqa: BLE001
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return model, os.cpu_count() or 1
+
+
+def oracle_seconds_per_pair(n_pairs=1, seed=0):
+    """Times the CPU oracle (restated reference arithmetic, torch-CPU fp32, all host threads)."""
+    import torch
+    from dsin_b200 import synth
+    from oracle import dsin_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Wt = synth.make_weights(0, residual_gamma=0.25)
+    x, y = synth.make_batch(n_pairs, H, W, seed=1000 + seed)
+    t0 = time.perf_counter()
+    O.reconstruct(x, y, Wt)
+    return (time.perf_counter() - t0) / n_pairs, cores
+
+
+def run_reference(args, rank):
+    """--impl reference: TF1 cannot run here, so the reference arm is the oracle's
+    restatement of the same arithmetic on the host cores; each step = one 320x1224 pair."""
+    if rank != 0:
+        return
+    model, cores = cpu_info()
+    for i in range(args.warmup if args.warmup < 1 else 1):  # one warm-up pair is enough on CPU
+        oracle_seconds_per_pair(1, seed=50 + i)
+    times = []
+    steps = max(1, min(args.steps, 3))
+    for i in range(steps):
+        s, cores = oracle_seconds_per_pair(1, seed=i)
+        times.append(s)
+    sec = float(np.mean(times))
+    mpix = H * W * 1e-6 / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mpix, "unit": "Mpixels/s", "n_gpus": 0,
+        "steps": steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "full inference (AE(y)+AE(x)+bpp+SI-Finder+SI-Net), 1 pair of 320x1224 per step; "
+                               "restated reference arithmetic (torch-CPU fp32) -- TF 1.11 itself is not runnable",
+                   "batch": 1, "H": H, "W": W},
+        "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": cores, "kind": "port",
+                         "sample": "%d x 1 pair 320x1224, full inference; CPU: %s" % (steps, model)},
+        "e2e": {"value": mpix, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def build_ae(device_index, residual_gamma=0.25):
+    from dsin_b200 import config_parser, synth
+    from dsin_b200.AE import AE
+    from dsin_b200.decoder_imgcomp import decoder
+    from dsin_b200.encoder_imgcomp import encoder
+    from dsin_b200.siFinder import siFinder
+    from dsin_b200.siFull_img import SI_full_img
+    from dsin_b200.siNet import siNet
+    cfg = os.path.join(ROOT, "dsin_b200", "run_configs")
+    ae_config, _ = config_parser.parse(os.path.join(cfg, "ae_run_configs"))
+    pc_config, _ = config_parser.parse(os.path.join(cfg, "pc_run_configs"))
+    Wt = synth.make_weights(0, residual_gamma=residual_gamma)
+    return AE(ae_config, pc_config, encoder, decoder, siFinder, SI_full_img, siNet, cfg, weights=Wt)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    from dsin_b200 import ops, synth
+    pk = peaks()
+    B = args.batch
+    ae = build_ae(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    # three distinct input batches per rank, rotated: 3 x 2 x B x 4.7 MB, together with the
+    # activations (>= 16 x 12.5 MB per layer) far beyond the 126 MB L2
+    NSETS = 3
+    host_sets = []
+    for s in range(NSETS):
+        x, y = synth.make_batch(B, H, W, seed=1000 * (rank + 1) + 17 * s)
+        px, py = ae.pinned_like(x.shape), ae.pinned_like(y.shape)
+        px.numpy()[...] = x
+        py.numpy()[...] = y
+        host_sets.append((px, py))
+    dev_sets = [(px.to(dev), py.to(dev)) for px, py in host_sets]
+
+    def step_device(i):
+        xd, yd = dev_sets[i % NSETS]
+        return ae.reconstruct_device(xd, yd)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident timing ----------------
+    for i in range(args.warmup):
+        out = step_device(i)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count()
+    ops.PROF.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    bits_total, npix_total = 0.0, 0
+    outs = []
+    for i in range(args.steps):
+        out = step_device(i)
+        outs.append(out["bits_sum"])
+    e1.record()
+    sync_all()
+    ops.PROF.stop()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    prof = ops.PROF.summary()
+    for bs in outs:
+        bits_total += float(bs.sum().item())
+        npix_total += B * H * W
+
+    # ---------------- end-to-end timing (public numpy API, pinned host buffers) ----------------
+    for i in range(min(2, args.warmup)):
+        ae.siNet_get_reconstructed(*host_sets[i % NSETS])
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        y_dec, y_syn, x_dec, x_with_si, bpp = ae.siNet_get_reconstructed(*host_sets[i % NSETS])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = 2 * B * 3 * H * W * 4
+    d2h = 4 * B * 3 * H * W * 4 + 8 * B
+
+    # ---------------- reductions over ranks ----------------
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    part = torch.tensor([bits_total, float(npix_total), float(B * args.steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros_like(part) for _ in range(world)]
+        dist.all_gather(gathered, part)  # the path's only collective
+        part = torch.stack(gathered).sum(0)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    pairs = B * args.steps * world
+    value = pairs * H * W * 1e-6 / (ms_max * 1e-3)
+    e2e_value = pairs * H * W * 1e-6 / (e2e_ms_max * 1e-3)
+
+    # ---------------- roofline of the dominant kernel ----------------
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else None
+    kern = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else None}
+            for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    roof = None
+    if top is not None:
+        name, v = top
+        ach = v["flops"] / (v["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " bf16 dense sustained",
+                "share_of_step": v["ms"] / sum(x["ms"] for x in prof.values()),
+                "avg_launch_ms": v["ms"] / v["launches"]}
+    whole = pairs / world * GFLOP_PER_PAIR_FULL / (ms_max * 1e-3) / 1e3  # TFLOP/s per GPU, algorithmic
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        sec, cores = oracle_seconds_per_pair(1)
+        model, _ = cpu_info()
+        cpu = {"value": H * W * 1e-6 / sec, "unit": "Mpixels/s", "cores": cores, "kind": "port",
+               "sample": "1 pair 320x1224 full inference, oracle torch-CPU fp32 (%.1f s); CPU: %s" % (sec, model)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": ae_dtype(), "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: full inference (AE(y)+AE(x)+bpp+SI-Finder+SI-Net) on "
+                               "batch %d of 320x1224 pairs per GPU, random-init KITTI_stereo_target_bpp0.02 shapes"
+                               % B, "batch_per_gpu": B, "H": H, "W": W, "patch": [PH, PW],
+                   "l2": "3 rotating input batches; activations per step >> 126 MB L2", "parallelism": "dp%d" % world},
+        "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms_max / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "whole_path_tflops_per_gpu": whole,
+        "whole_path_frac_of_bf16_sustained": whole / pk["tf_sust"],
+        "kernels": kern,
+        "cpu_baseline": cpu,
+        "bpp_aggregate": float(part[0] / part[1]) if float(part[1]) else None,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def ae_dtype():
+    from dsin_b200 import autoencoder_imgcomp
+    return getattr(autoencoder_imgcomp, "COMPUTE_DTYPE", "f32")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

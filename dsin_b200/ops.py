@@ -38,6 +38,49 @@ def _chk(t, dtype=torch.float32):
     return t
 
 
+class _Profiler(object):
+    """Optional per-kernel CUDA-event timing (bench.py's roofline): when enabled every wrapped
+    launch is bracketed by events on the launching stream and tagged with its algorithmic FLOPs."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []
+
+    def start(self):
+        self.enabled, self.records = True, []
+
+    def stop(self):
+        self.enabled = False
+
+    def begin(self):
+        if not self.enabled:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, e0, name, flops=0.0, bytes_=0.0):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.records.append((name, e0, e1, flops, bytes_))
+
+    def summary(self):
+        """name -> dict(ms, launches, flops, bytes); call after a device synchronise."""
+        out = {}
+        for name, e0, e1, fl, by in self.records:
+            d = out.setdefault(name, dict(ms=0.0, launches=0, flops=0.0, bytes=0.0))
+            d["ms"] += e0.elapsed_time(e1)
+            d["launches"] += 1
+            d["flops"] += fl
+            d["bytes"] += by
+        return out
+
+
+PROF = _Profiler()
+
+
 def launch_count():
     return sum(h.launch_count() for h in _handles.values())
 
@@ -100,8 +143,15 @@ def conv2d(x, layer, res1=None, res2=None, scale=None, shift=None, act=None, pos
         assert res1.shape == y.shape
     if res2 is not None:
         assert res2.shape == y.shape
+    e0 = PROF.begin()
     h.check(h.lib.dsin_conv2d(h.ptr, C.byref(d), _p(_chk(x)), _p(layer.w), _p(sc), _p(sh), _p(res1), _p(res2),
                               _p(y), _stream()))
+    if e0 is not None:
+        pix = n * (hh * ww if layer.transposed else oh * ow)  # direct-form dense MACs
+        PROF.end(e0, "conv%dx%d_%dto%d%s%s" % (layer.kh, layer.kw, cin, layer.cout,
+                                                "_T" if layer.transposed else ("_s%d" % layer.stride),
+                                                "_d" if layer.dilation > 1 else ""),
+                 2.0 * pix * layer.kh * layer.kw * cin * layer.cout)
     return y
 
 
@@ -130,8 +180,13 @@ def probclass_bits(qbar_nchw, symbols, weights, pad_value, k=24, L=6, want_bits=
     flat = []
     for w, b in weights:
         flat += [_p(_chk(w)), _p(_chk(b))]
+    e0 = PROF.begin()
     h.check(h.lib.dsin_probclass_bits(h.ptr, _p(_chk(qbar_nchw)), _p(_chk(symbols, torch.int64)), n, c, hh, ww, k, L,
                                       C.c_float(float(pad_value)), *flat, _p(bits), _p(sums), _p(work), _stream()))
+    if e0 is not None:
+        vox = lambda a, b_, c_: float(n * (c + a) * (hh + b_) * (ww + c_))  # noqa: E731
+        PROF.end(e0, "probclass", 2.0 * 18 * (vox(3, 6, 6) * k + vox(2, 4, 4) * k * k + vox(1, 2, 2) * k * k
+                                              + vox(0, 0, 0) * k * L))
     return bits, sums
 
 
@@ -159,8 +214,11 @@ def sif_match(q, r, pstat, ystat, ph, pw, use_mask=True, method=0):
     row = torch.empty((n, P), dtype=torch.int32, device=dev)
     col = torch.empty((n, P), dtype=torch.int32, device=dev)
     best = torch.empty((n, P), dtype=torch.float32, device=dev)
+    e0 = PROF.begin()
     h.check(h.lib.dsin_sif_match(h.ptr, _p(_chk(q)), _p(_chk(r)), _p(_chk(pstat)), _p(_chk(ystat)), n, hh, ww, ph, pw,
                                  int(use_mask), int(method), _p(row), _p(col), _p(best), _p(work), _stream()))
+    if e0 is not None:
+        PROF.end(e0, "sif_match", 2.0 * n * (hh - ph + 1) * (ww - pw + 1) * P * (ph * pw * 3))
     return row, col, best
 
 
