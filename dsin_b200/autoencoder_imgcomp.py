@@ -20,6 +20,13 @@ EncoderOutput = namedtuple("EncoderOutput", ["qbar", "qhard", "symbols", "z", "h
 BN_EPS = np.float32(1e-5)
 arch_param_n = 128
 
+# How the 64 trunk convs (3x3, 128->128) run:
+#   "tc3"  tcgen05, split-fp16 operands, 3 MMAs per product (fp32-class; the parity mode)
+#   "tc1"  tcgen05, fp16 operands, 1 MMA (fast mode; symbols no longer bit-exact)
+#   "simt" CUDA-core fp32 (v1 kernel, kept as the on-GPU cross-check)
+TRUNK_MODE = "tc3"
+COMPUTE_DTYPE = "f16x2-split tensor-core (fp32 accumulate) + f32 CUDA-core"
+
 
 def get_network_cls(config):
     return {"CVPR": _CVPR}[config.arch]
@@ -41,6 +48,7 @@ class _Network(object):
         self.num_chan_bn_including_heatmap = config.num_chan_bn + 1
         self._centers = None
         self.layers = {}
+        self._tc_layers = {}
         self.device = "cuda"
 
     @staticmethod
@@ -84,6 +92,7 @@ class _CVPR(_Network):
     def load_weights(self, W):
         B = self.config.arch_param_B
         E, D = synth.ENC, synth.DEC
+        self._tc_layers = {}
         self._centers = torch.from_numpy(np.ascontiguousarray(W[E + "centers"], np.float32)).to(self.device)
         self.centers_host = np.asarray(W[E + "centers"], np.float32).copy()
         self._conv(W, E + "h1", stride=2)
@@ -103,7 +112,29 @@ class _CVPR(_Network):
             self._conv(W, pre + fin + "/conv2", relu=False)
 
     # -- trunk: 15 residual blocks + final block, 3 skip levels (shared by enc and dec) --------
+    def _tc(self, scope):
+        t = self._tc_layers.get(scope)
+        if t is None:
+            t = self._tc_layers[scope] = ops.Conv3x3TC(self.layers[scope])
+        return t
+
+    def _trunk_tc(self, net, pre, blk, fin, terms):
+        cur = ops.f32_to_split(net)
+        r0 = cur
+        for b in range(self.config.arch_param_B):
+            rb = cur
+            for i in (1, 2, 3):
+                sc = pre + blk % (b, b, i)
+                t = ops.conv3x3_tc(cur[0], cur[1], self._tc(sc + "/conv1"), terms=terms)
+                cur = ops.conv3x3_tc(t[0], t[1], self._tc(sc + "/conv2"), res1=cur, res2=rb if i == 3 else None,
+                                     terms=terms)
+        t = ops.conv3x3_tc(cur[0], cur[1], self._tc(pre + fin + "/conv1"), terms=terms)
+        cur = ops.conv3x3_tc(t[0], t[1], self._tc(pre + fin + "/conv2"), res1=cur, res2=r0, terms=terms)
+        return ops.split_to_f32(cur[0], cur[1])
+
     def _trunk(self, net, pre, blk, fin):
+        if TRUNK_MODE in ("tc3", "tc1") and net.shape[1] >= 8 and net.shape[2] >= 16:
+            return self._trunk_tc(net, pre, blk, fin, 3 if TRUNK_MODE == "tc3" else 1)
         L = self.layers
         r0 = net
         for b in range(self.config.arch_param_B):

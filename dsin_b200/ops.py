@@ -155,6 +155,60 @@ def conv2d(x, layer, res1=None, res2=None, scale=None, shift=None, act=None, pos
     return y
 
 
+def f32_to_split(x):
+    """fp32 tensor -> (hi, lo) fp16 planes with x ~= hi + lo (22-bit)."""
+    h = handle()
+    hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    h.check(h.lib.dsin_f32_to_split(h.ptr, _p(_chk(x)), _p(hi), _p(lo), x.numel(), _stream()))
+    return hi, lo
+
+
+def split_to_f32(hi, lo):
+    h = handle()
+    y = torch.empty(hi.shape, dtype=torch.float32, device=hi.device)
+    h.check(h.lib.dsin_split_to_f32(h.ptr, _p(_chk(hi, torch.float16)), _p(_chk(lo, torch.float16)), _p(y),
+                                    hi.numel(), _stream()))
+    return y
+
+
+class Conv3x3TC(object):
+    """Tensor-core form of a 3x3 128->128 ConvLayer: weights packed [tap][cout][cin] as split fp16 with a
+    per-cout power-of-two scale that is folded back into the epilogue scale (exact)."""
+
+    def __init__(self, layer):
+        assert (layer.kh, layer.kw, layer.cin, layer.cout) == (3, 3, 128, 128) and layer.stride == 1
+        assert layer.dilation == 1 and not layer.transposed
+        h = handle()
+        dev = layer.w.device
+        self.w_hi = torch.empty((9, 128, 128), dtype=torch.float16, device=dev)
+        self.w_lo = torch.empty((9, 128, 128), dtype=torch.float16, device=dev)
+        wscale = torch.empty((128,), dtype=torch.float32, device=dev)
+        h.check(h.lib.dsin_pack_conv3x3_w(h.ptr, _p(layer.w), _p(self.w_hi), _p(self.w_lo), _p(wscale), 128, 128,
+                                          _stream()))
+        self.scale = (layer.scale / wscale).contiguous()  # power-of-two division: exact
+        self.shift = layer.shift
+        self.act = layer.act
+
+
+def conv3x3_tc(xh, xl, tcl, res1=None, res2=None, terms=3):
+    """Split-fp16 NHWC in/out; res1/res2 are (hi, lo) pairs or None."""
+    h = handle()
+    n, hh, ww, c = xh.shape
+    assert c == 128
+    yh = torch.empty_like(xh)
+    yl = torch.empty_like(xh)
+    r1h, r1l = res1 if res1 is not None else (None, None)
+    r2h, r2l = res2 if res2 is not None else (None, None)
+    e0 = PROF.begin()
+    h.check(h.lib.dsin_conv3x3_c128_tc(h.ptr, n, hh, ww, _p(_chk(xh, torch.float16)), _p(xl), _p(tcl.w_hi),
+                                       _p(tcl.w_lo), _p(tcl.scale), _p(tcl.shift), tcl.act, _p(r1h), _p(r1l),
+                                       _p(r2h), _p(r2l), _p(yh), _p(yl), terms, _stream()))
+    if e0 is not None:
+        PROF.end(e0, "conv3x3_128to128_tc%d" % terms, 2.0 * n * hh * ww * 9 * 128 * 128)
+    return yh, yl
+
+
 def heatmap_quantize(z33_nhwc, centers):
     h = handle()
     n, hh, ww, c1 = z33_nhwc.shape

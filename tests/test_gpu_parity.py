@@ -243,3 +243,35 @@ def test_stagewise_and_free_running_full_size():
           "rowcol agree %.4f" % (float(bpp), float(ref.bpp), a, b, a2, b2, agree))
     assert abs(float(bpp) - float(ref.bpp)) <= 1e-5 * (1 + 4 * n_mism)
     assert abs(a - b) <= 1e-4 * (1 + 4 * n_mism) and abs(a2 - b2) <= 1e-4 * (1 + 4 * n_mism)
+
+
+# ----------------------------------------------------------------------------- tcgen05 trunk conv
+@pytest.mark.parametrize("terms,tol", [(3, 1e-5), (1, 3e-3)])  # 1e-5: fp32 accumulation over K=1152
+@pytest.mark.parametrize("shape", [(2, 20, 36), (1, 80, 306), (3, 9, 17)])
+def test_conv3x3_tc_matches_fp32_conv(terms, tol, shape):
+    """tcgen05 3x3 128->128 conv (split-fp16) vs the oracle's fp32 conv on the same (split-rounded) input."""
+    from dsin_b200 import ops
+    rng = np.random.default_rng(7)
+    n, hh, ww = shape
+    x = rng.standard_normal((n, 128, hh, ww)).astype(np.float32)
+    w = (rng.standard_normal((3, 3, 128, 128)) / np.sqrt(9 * 128)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, 128).astype(np.float32)
+    shift = rng.standard_normal(128).astype(np.float32)
+    r1 = rng.standard_normal((n, 128, hh, ww)).astype(np.float32)
+    r2 = rng.standard_normal((n, 128, hh, ww)).astype(np.float32)
+    layer = ops.ConvLayer(w, scale, shift, act=ops.ACT_RELU)
+    tcl = ops.Conv3x3TC(layer)
+    xs = ops.f32_to_split(_nhwc(_dev(x)))
+    r1s = ops.f32_to_split(_nhwc(_dev(r1)))
+    r2s = ops.f32_to_split(_nhwc(_dev(r2)))
+    yh, yl = ops.conv3x3_tc(xs[0], xs[1], tcl, res1=r1s, res2=r2s, terms=terms)
+    got = ops.split_to_f32(yh, yl).permute(0, 3, 1, 2).cpu().double()
+    # reference in float64 from the values the kernel actually saw
+    xq = ops.split_to_f32(*xs).permute(0, 3, 1, 2).cpu().double()
+    r1q = ops.split_to_f32(*r1s).permute(0, 3, 1, 2).cpu().double()
+    r2q = ops.split_to_f32(*r2s).permute(0, 3, 1, 2).cpu().double()
+    ref = O.conv2d_same(xq, w.astype(np.float64))
+    ref = torch.relu(ref * torch.tensor(scale).double().view(1, -1, 1, 1) + torch.tensor(shift).double().view(1, -1, 1, 1))
+    ref = ref + r1q + r2q
+    err = float((got - ref).abs().max())
+    assert err < tol * max(1.0, float(ref.abs().max())), err
