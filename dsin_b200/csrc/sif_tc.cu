@@ -1,9 +1,428 @@
-// tcgen05 SI-Finder scorer (placeholder until the tensor-core path lands).
+// K6 on tensor cores: SI-Finder all-pairs patch correlation as a tcgen05 implicit GEMM with a fused
+// Pearson / Gaussian-prior / running-top-k epilogue, followed by exact rescoring of the candidates.
+//   replaces L2_or_pearson_corr + mask multiply + argmax (src/siFinder.py:76-135,20,27-33).
+//
+// GEMM per image: D[P patches x (h*w) positions] = Q[P x K] * R_windows[(h*w) x K]^T, K = ph*pw*3.
+//   M axis = patches (one TMEM lane = one patch  ->  the argmax over positions is a per-thread
+//            running reduction over TMEM columns, no cross-thread traffic);
+//   N axis = 256 consecutive positions of one correlation row.
+// The position operand is Toeplitz (window j+1 = window j shifted by one pixel).  It is fed ZERO-COPY:
+// the search image is stored as 16-byte "pixels" S[y][x] = fp16 {r(y,x,0..2), r(y+1,x,0..2), 0, 0};
+// one TMA box brings a strip of 280 such pixels into shared memory, and a no-swizzle K-major UMMA
+// descriptor with LBO = 16 B (next K chunk = next pixel) and SBO = 128 B (next 8 positions) makes row n
+// of the operand start 16*n bytes into the strip -- overlapping windows, no im2col.  One K=16 MMA step
+// consumes two pixels x two image rows; a patch-row pair is 24 px = 12 steps; 10 pairs per patch.
+// (6 of 8 K slots carry data: 75 % K efficiency, the price of the 16-byte row pitch.)
+// Patches are pre-centred per patch (q - mean_q) before the fp16 rounding, which removes the large
+// cancellation in the Pearson numerator; the coarse score error is ~1e-4.  Each work unit (image,
+// patch tile, 8 correlation rows) keeps the 4 best coarse candidates per patch; a second kernel rescored
+// every candidate within DELTA of the coarse best with the reference's exact arithmetic (fp32 data,
+// fp64 dot product, literal fp32 Pearson algebra, exact fp64->fp32 prior) and takes the first maximum.
 #include "sif_common.cuh"
+#include "tc_common.cuh"
 
-int64_t sif_tc_workspace_bytes(int n, int hh, int ww, int ph, int pw, int method) { return 0; }
+using namespace tc;
 
-int sif_tc_match(dsin_handle_t h, const float*, const float*, const float*, const float*, int, int, int, int,
-                 int, int, unsigned long long*, void*, cudaStream_t) {
-  return dsin_fail(h, DSIN_ERR_UNSUPPORTED, "%s: tensor-core SI-Finder not built", __func__);
+namespace {
+
+constexpr int TN = 256;                 // positions per tile
+constexpr int PAIRS = 10;               // patch-row pairs (ph = 20)
+constexpr int PWX = 24;                 // patch width in pixels
+constexpr int KQ = PAIRS * PWX * 8;     // packed K per patch (1920 fp16)
+constexpr int A_BYTES = 3 * 128 * 128;  // three [128 patches x 64 k] SW128 tiles per pair = 48 KB
+constexpr int STRIP_PIX = 280;          // 256 + 24 pixels (even count; 23 needed)
+constexpr int B_BYTES = STRIP_PIX * 16; // 4480
+constexpr int STAGE_BYTES = A_BYTES + 5120;
+constexpr int STAGES = 4;
+constexpr int ROWS_PER_UNIT = 8;
+constexpr int TOPK = 4;
+constexpr float DELTA = 2e-3f;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * TN * 8 + 1024 /*align*/ + 512 /*barriers*/;
+
+struct SifP {
+  const float4* ystat;   // (n,hp,wp): sum_y, mean_y, den_y, sum_y2
+  const float4* pinfo;   // (n,P): sum of fp16 centred patch, rsqrt(den_x), cy', cx'
+  float2* cand;          // (n,P,units,TOPK): coarse score, position index (as int bits)
+  int n, hp, wp, P, ptiles, rgroups, jtiles, total_units, use_mask;
+  float kh, kw;          // -4/sigma_h^2, -4/sigma_w^2 (exp2 form of exp(-4 ln2 t))
+};
+
+__global__ void __launch_bounds__(192, 1)
+sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_s, SifP p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* tiles = smem;
+  float2* s_pos = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES);  // [2][TN]: mean_y, rsqrt(den_y)
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_pos + 2 * TN);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tm_q);
+    prefetch_tmap(&tm_s);
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int units_per_img = p.ptiles * p.rgroups;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        const int img = u / units_per_img, r = u % units_per_img;
+        const int pt = r / p.rgroups, rg = r % p.rgroups;
+        const int i1 = min(p.hp, (rg + 1) * ROWS_PER_UNIT);
+        for (int i = rg * ROWS_PER_UNIT; i < i1; ++i)
+          for (int jt = 0; jt < p.jtiles; ++jt)
+            for (int d = 0; d < PAIRS; ++d) {
+              mbar_wait(&empty[stage], phase ^ 1u);
+              uint8_t* st = tiles + stage * STAGE_BYTES;
+              mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+                tma_load_3d(st + c * 16384, &tm_q, &full[stage], d * 192 + c * 64, pt * 128, img);
+              tma_load_4d(st + A_BYTES, &tm_s, &full[stage], 0, jt * (TN / 2), i + 2 * d, img);
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, TN, 0);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        const int rg = (u % units_per_img) % p.rgroups;
+        const int i1 = min(p.hp, (rg + 1) * ROWS_PER_UNIT);
+        for (int i = rg * ROWS_PER_UNIT; i < i1; ++i)
+          for (int jt = 0; jt < p.jtiles; ++jt, ++it) {
+            const int acc = it & 1;
+            mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            fence_after_sync();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * TN;
+            for (int d = 0; d < PAIRS; ++d) {
+              mbar_wait(&full[stage], phase);
+              fence_after_sync();
+              const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES);
+              const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+              for (int s = 0; s < 12; ++s) {
+                // A: chunk s/4 (16 KB, SW128), K step s%4 (+32 B).  B: Toeplitz strip, pixels 2s, 2s+1.
+                const uint64_t da = make_smem_desc(sa + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024, LAYOUT_SW128);
+                const uint64_t db = make_smem_desc(sb + s * 32, 16, 128, LAYOUT_NONE);
+                umma_f16(d_tmem, da, db, idesc, (d | s) ? 1u : 0u);
+              }
+              umma_commit(&empty[stage]);
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+            umma_commit(&tfull[acc]);
+          }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps 2..5
+    const int q = warp & 3;
+    const int et = (warp - 2) * 32 + lane;  // 0..127 among epilogue threads
+    int it = 0;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      const int img = u / units_per_img, r = u % units_per_img;
+      const int pt = r / p.rgroups, rg = r % p.rgroups;
+      const int pch = pt * 128 + q * 32 + lane;
+      const bool pvalid = pch < p.P;
+      float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pvalid) pi = p.pinfo[(size_t)img * p.P + pch];
+      float bs[TOPK];
+      int bi[TOPK];
+#pragma unroll
+      for (int k = 0; k < TOPK; ++k) {
+        bs[k] = -INFINITY;
+        bi[k] = -1;
+      }
+      const int i1 = min(p.hp, (rg + 1) * ROWS_PER_UNIT);
+      for (int i = rg * ROWS_PER_UNIT; i < i1; ++i) {
+        float rowf = pi.y;  // rsqrt(den_x) * row factor of the prior
+        if (p.use_mask) {
+          float dh = (float)i - pi.z;
+          rowf *= exp2f(p.kh * dh * dh);
+        }
+        for (int jt = 0; jt < p.jtiles; ++jt, ++it) {
+          const int acc = it & 1;
+          const int j0 = jt * TN;
+          const int nvalid = min(TN, p.wp - j0);
+          // stage per-position statistics for this tile (double buffered with the accumulator)
+          float2* sp = s_pos + acc * TN;
+#pragma unroll
+          for (int c = et; c < TN; c += 128) {
+            float2 v = make_float2(0.f, 0.f);
+            if (c < nvalid) {
+              float4 ys = __ldg(p.ystat + ((size_t)img * p.hp + i) * p.wp + j0 + c);
+              v.x = ys.y;
+              v.y = ys.z > 0.f ? rsqrtf(ys.z) : 0.f;
+            }
+            sp[c] = v;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u);
+          fence_after_sync();
+#pragma unroll 1
+          for (int chunk = 0; chunk < TN / 32; ++chunk) {
+            if (chunk * 32 >= nvalid) break;  // warp-uniform
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + chunk * 32), v);
+            tmem_ld_wait();
+            if (pvalid) {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) {
+                const int c = chunk * 32 + jj;
+                const float2 ps = sp[c];
+                float s = (__uint_as_float(v[jj]) - ps.x * pi.x) * ps.y * rowf;
+                if (p.use_mask) {
+                  float dw = (float)(j0 + c) - pi.w;
+                  s *= exp2f(p.kw * dw * dw);
+                }
+                if (c < nvalid && s > bs[TOPK - 1]) {
+                  const int idx = i * p.wp + j0 + c;
+                  if (s > bs[0]) {
+                    bs[3] = bs[2]; bi[3] = bi[2]; bs[2] = bs[1]; bi[2] = bi[1]; bs[1] = bs[0]; bi[1] = bi[0];
+                    bs[0] = s; bi[0] = idx;
+                  } else if (s > bs[1]) {
+                    bs[3] = bs[2]; bi[3] = bi[2]; bs[2] = bs[1]; bi[2] = bi[1];
+                    bs[1] = s; bi[1] = idx;
+                  } else if (s > bs[2]) {
+                    bs[3] = bs[2]; bi[3] = bi[2];
+                    bs[2] = s; bi[2] = idx;
+                  } else {
+                    bs[3] = s; bi[3] = idx;
+                  }
+                }
+              }
+            }
+          }
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+      }
+      if (pvalid) {
+        float2* dst = p.cand + (((size_t)img * p.P + pch) * p.rgroups + rg) * TOPK;
+#pragma unroll
+        for (int k = 0; k < TOPK; ++k) dst[k] = make_float2(bs[k], __int_as_float(bi[k]));
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- operand packing -------------------------------------------------------------------------
+// one warp per patch: centred fp16 patch in the paired-row 16-byte-pixel layout + per-patch info
+__global__ void sif_pack_q_kernel(const float* __restrict__ q, const float* __restrict__ pstat,
+                                  __half* __restrict__ q2, float4* __restrict__ pinfo, int n, int P, int ph,
+                                  int pw, int hh, int ww) {
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
+  if (wid >= (int64_t)n * P) return;
+  const int pch = (int)(wid % P);
+  const float* qp = q + wid * (ph * pw * 3);
+  const float xm = pstat[wid * 4 + 2];
+  float s16 = 0.f;
+  __half* out = q2 + wid * KQ;
+  for (int e = lane; e < (ph / 2) * pw; e += 32) {  // (pair d, pixel px)
+    const int d = e / pw, px = e % pw;
+    __half hv[8];
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+      const int dy = 2 * d + t / 3, c = t % 3;
+      __half hq = __float2half_rn(qp[(dy * pw + px) * 3 + c] - xm);
+      hv[t] = hq;
+      s16 += __half2float(hq);
+    }
+    hv[6] = hv[7] = __float2half_rn(0.f);
+    *reinterpret_cast<uint4*>(out + (size_t)e * 8) = *reinterpret_cast<const uint4*>(hv);
+  }
+  for (int o = 16; o > 0; o >>= 1) s16 += __shfl_xor_sync(0xffffffffu, s16, o);
+  if (lane == 0) {
+    const float denx = pstat[wid * 4 + 3];
+    const int pcs = ww / pw;
+    const float cy = ((float)(pch / pcs) + 0.5f) * ph - (float)(ph / 2 - 1);
+    const float cx = ((float)(pch % pcs) + 0.5f) * pw - (float)(pw / 2 - 1);
+    pinfo[wid] = make_float4(s16, denx > 0.f ? rsqrtf(denx) : 0.f, cy, cx);
+  }
+}
+
+// S[y][x] = {r(y,x,0..2), r(y+1,x,0..2), 0, 0} as fp16, y in [0, hh-1)
+__global__ void sif_pack_strip_kernel(const float* __restrict__ r, __half* __restrict__ s, int n, int hh,
+                                      int ww) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n * (hh - 1) * ww) return;
+  const int x = (int)(idx % ww);
+  const int64_t t = idx / ww;
+  const int y = (int)(t % (hh - 1));
+  const int img = (int)(t / (hh - 1));
+  const float* a = r + (((int64_t)img * hh + y) * ww + x) * 3;
+  const float* b = a + (int64_t)ww * 3;
+  __half hv[8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    hv[c] = __float2half_rn(a[c]);
+    hv[3 + c] = __float2half_rn(b[c]);
+  }
+  hv[6] = hv[7] = __float2half_rn(0.f);
+  reinterpret_cast<uint4*>(s)[idx] = *reinterpret_cast<const uint4*>(hv);
+}
+
+// ---- exact rescoring: one warp per (image, patch) ------------------------------------------------
+__global__ void sif_rescore_kernel(const float2* __restrict__ cand, int ncand, const float* __restrict__ q,
+                                   const float* __restrict__ r, const float* __restrict__ pstat,
+                                   const float* __restrict__ ystat, int n, int hh, int ww, int ph, int pw,
+                                   int use_mask, unsigned long long* __restrict__ keys) {
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
+  const int P = (hh / ph) * (ww / pw);
+  if (wid >= (int64_t)n * P) return;
+  const int img = (int)(wid / P), pch = (int)(wid % P);
+  const int wp = ww - pw + 1, hp = hh - ph + 1;
+  const int kdim = ph * pw * 3, krow = pw * 3;
+  const float2* cp = cand + wid * ncand;
+  float best = -INFINITY;
+  for (int c = lane; c < ncand; c += 32) best = fmaxf(best, cp[c].x);
+  for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+  const float thr = best - DELTA;
+  const float* qp = q + wid * kdim;
+  const float* ps = pstat + wid * 4;
+  unsigned long long key = 0ull;
+  for (int c = 0; c < ncand; ++c) {
+    const float2 cv = cp[c];
+    const int idx = __float_as_int(cv.y);
+    if (!(cv.x >= thr) || idx < 0) continue;  // warp-uniform
+    const int i = idx / wp, j = idx % wp;
+    const float* rp = r + (((int64_t)img * hh + i) * ww + j) * 3;
+    double acc = 0.0;
+    for (int k = lane; k < kdim; k += 32) {
+      const int dy = k / krow, kk = k - dy * krow;
+      acc += (double)qp[k] * (double)__ldg(rp + (int64_t)dy * ww * 3 + kk);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const float4 ys = reinterpret_cast<const float4*>(ystat)[((int64_t)img * hp + i) * wp + j];
+      float s = sif_pearson((float)acc, ys.x, ys.y, ys.z, ps[0], ps[2], ps[3], (float)kdim);
+      if (use_mask) s = __fmul_rn(s, sif_mask_exact(pch, i, j, hh, ww, ph, pw));
+      const unsigned long long k2 = sif_pack(s, (unsigned)idx);
+      key = k2 > key ? k2 : key;
+    }
+  }
+  if (lane == 0) keys[wid] = key;
+}
+
+struct Layout {
+  int64_t q2, strip, pinfo, cand, total;
+  int ptiles, rgroups, jtiles, ncand;
+};
+
+Layout make_layout(int n, int hh, int ww, int ph, int pw) {
+  Layout L;
+  const int P = (hh / ph) * (ww / pw), hp = hh - ph + 1, wp = ww - pw + 1;
+  L.ptiles = (P + 127) / 128;
+  L.rgroups = (hp + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+  L.jtiles = (wp + TN - 1) / TN;
+  L.ncand = L.rgroups * TOPK;
+  auto up = [](int64_t v) { return (v + 1023) / 1024 * 1024; };
+  L.q2 = 0;
+  L.strip = up((int64_t)n * P * KQ * 2);
+  L.pinfo = L.strip + up((int64_t)n * (hh - 1) * ww * 16);
+  L.cand = L.pinfo + up((int64_t)n * P * 16);
+  L.total = L.cand + up((int64_t)n * P * L.ncand * 8);
+  return L;
+}
+
+}  // namespace
+
+int64_t sif_tc_workspace_bytes(int n, int hh, int ww, int ph, int pw, int method) {
+  if (method == 0) return 0;
+  return make_layout(n, hh, ww, ph, pw).total + 1024;
+}
+
+int sif_tc_match(dsin_handle_t h, const float* q, const float* r, const float* pstat, const float* ystat, int n,
+                 int hh, int ww, int ph, int pw, int use_mask, unsigned long long* keys, void* ws, cudaStream_t st) {
+  if (ph != 2 * PAIRS || pw != PWX)
+    return dsin_fail(h, DSIN_ERR_UNSUPPORTED, "%s: tensor-core SI-Finder is built for 20x24 patches", __func__);
+  if (ww % 2 != 0) return dsin_fail(h, DSIN_ERR_UNSUPPORTED, "%s: image width must be even", __func__);
+  const int P = (hh / ph) * (ww / pw), hp = hh - ph + 1, wp = ww - pw + 1;
+  const Layout L = make_layout(n, hh, ww, ph, pw);
+  uint8_t* base = (uint8_t*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  __half* q2 = (__half*)(base + L.q2);
+  __half* strip = (__half*)(base + L.strip);
+  float4* pinfo = (float4*)(base + L.pinfo);
+  float2* cand = (float2*)(base + L.cand);
+
+  const int64_t np = (int64_t)n * P;
+  sif_pack_q_kernel<<<(unsigned)((np * 32 + 255) / 256), 256, 0, st>>>(q, pstat, q2, pinfo, n, P, ph, pw, hh, ww);
+  DSIN_LAUNCHED(h);
+  const int64_t ns = (int64_t)n * (hh - 1) * ww;
+  sif_pack_strip_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(r, strip, n, hh, ww);
+  DSIN_LAUNCHED(h);
+
+  CUtensorMap tm_q, tm_s;
+  const uint64_t qd[3] = {(uint64_t)KQ, (uint64_t)P, (uint64_t)n};
+  const uint64_t qs[2] = {(uint64_t)KQ * 2, (uint64_t)P * KQ * 2};
+  const uint32_t qb[3] = {64, 128, 1};
+  const uint64_t sd[4] = {16, (uint64_t)ww / 2, (uint64_t)(hh - 1), (uint64_t)n};
+  const uint64_t ss[3] = {32, (uint64_t)ww * 16, (uint64_t)(hh - 1) * ww * 16};
+  const uint32_t sb[4] = {16, STRIP_PIX / 2, 1, 1};
+  if (!encode_tmap(&tm_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, q2, qd, qs, qb, CU_TENSOR_MAP_SWIZZLE_128B) ||
+      !encode_tmap(&tm_s, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, strip, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_NONE))
+    return dsin_fail(h, DSIN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", __func__);
+
+  SifP p;
+  p.ystat = (const float4*)ystat;
+  p.pinfo = pinfo;
+  p.cand = cand;
+  p.n = n; p.hp = hp; p.wp = wp; p.P = P;
+  p.ptiles = L.ptiles; p.rgroups = L.rgroups; p.jtiles = L.jtiles;
+  p.total_units = n * L.ptiles * L.rgroups;
+  p.use_mask = use_mask;
+  p.kh = -4.0f / ((0.5f * hh) * (0.5f * hh));
+  p.kw = -4.0f / ((0.5f * ww) * (0.5f * ww));
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(sif_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+      return dsin_fail(h, DSIN_ERR_CUDA, "%s: cannot raise dynamic shared memory", __func__);
+    configured = true;
+  }
+  const int grid = p.total_units < h->sm_count ? p.total_units : h->sm_count;
+  sif_tc_kernel<<<grid, 192, SMEM_BYTES, st>>>(tm_q, tm_s, p);
+  DSIN_LAUNCHED(h);
+  sif_rescore_kernel<<<(unsigned)((np * 32 + 255) / 256), 256, 0, st>>>(cand, L.ncand, q, r, pstat, ystat, n, hh, ww,
+                                                                   ph, pw, use_mask, keys);
+  DSIN_LAUNCHED(h);
+  return DSIN_OK;
 }

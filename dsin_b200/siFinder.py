@@ -11,7 +11,7 @@ import torch
 
 from . import ops
 
-METHOD = 0  # 0: fp32 SIMT scorer; 1: tcgen05 coarse scorer + exact rescoring
+METHOD = 1  # 0: fp32 SIMT scorer (cross-check); 1: tcgen05 coarse scorer + exact rescoring
 
 
 class GaussianPrior(object):

@@ -114,8 +114,17 @@ def _sif_case(H, W, seed, n=2):
     return np.stack(xs), np.stack(ys)
 
 
+@pytest.fixture(params=[0, 1], ids=["simt", "tcgen05"])
+def sif_method(request):
+    from dsin_b200 import siFinder as sf
+    old = sf.METHOD
+    sf.METHOD = request.param
+    yield request.param
+    sf.METHOD = old
+
+
 @pytest.mark.parametrize("hw", [(80, 144), (120, 96)])
-def test_sifinder_rowcol_and_gather_match_oracle(hw):
+def test_sifinder_rowcol_and_gather_match_oracle(hw, sif_method):
     from dsin_b200.siFinder import match_images
     H, W = hw
     x, y = _sif_case(H, W, 10)
@@ -162,7 +171,27 @@ def _adjudicate_rowcol(x_dec, y_dec, row, col, ref_row, ref_col, tol=2e-6):
     return mism
 
 
-def test_sifinder_flat_rgb_patch_matches_oracle():
+def test_sifinder_tc_equals_simt_full_size():
+    """320x1224, 2 structured pairs: tcgen05 coarse + exact rescoring vs the fp32 SIMT scorer."""
+    from dsin_b200 import siFinder as sf
+    x, y = _sif_case(320, 1224, 40)
+    args = (_nhwc(_dev(x)), _nhwc(_dev(y)), _nhwc(_dev(y)), 20, 24, True)
+    old = sf.METHOD
+    try:
+        sf.METHOD = 0
+        _, _, _, row0, col0, best0 = sf.match_images(*args)
+        sf.METHOD = 1
+        _, _, _, row1, col1, best1 = sf.match_images(*args)
+    finally:
+        sf.METHOD = old
+    mism = _adjudicate_rowcol(x, y, row1.cpu(), col1.cpu(), row0.cpu(), col0.cpu(), tol=3e-6)
+    print("tc vs simt: %d / %d positions differ (all float64 near-ties)" % (int(mism.sum()), mism.numel()))
+    assert int(mism.sum()) <= 4
+    same = ~mism
+    assert float((best1.cpu() - best0.cpu())[same].abs().max()) < 2e-5
+
+
+def test_sifinder_flat_rgb_patch_matches_oracle(sif_method):
     """A patch that is constant in RGB is NOT degenerate: after the per-channel normalisation and
     colour transform its 1440-vector still varies across channels (den_x > 0)."""
     from dsin_b200.siFinder import match_images
