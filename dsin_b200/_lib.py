@@ -41,6 +41,9 @@ SIGNATURES = {
     "dsin_conv2d": (_I, [_P, C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "dsin_pack_conv3x3_w": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "dsin_conv3x3_c128_tc": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "dsin_conv_tc_npad": (_I, [_I]),
+    "dsin_pack_conv_w_tc": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "dsin_conv2d_tc": (_I, [_P, C.POINTER(ConvDesc), _I] + [_P] * 14),
     "dsin_f32_to_split": (_I, [_P, _P, _P, _P, _I64, _P]),
     "dsin_split_to_f32": (_I, [_P, _P, _P, _P, _I64, _P]),
     "dsin_heatmap_quantize": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),

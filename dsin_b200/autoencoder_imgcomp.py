@@ -111,30 +111,53 @@ class _CVPR(_Network):
             self._conv(W, pre + fin + "/conv1", relu=False)  # activation_fn=None on both
             self._conv(W, pre + fin + "/conv2", relu=False)
 
-    # -- trunk: 15 residual blocks + final block, 3 skip levels (shared by enc and dec) --------
+    # -- tensor-core path --------------------------------------------------------------------
     def _tc(self, scope):
         t = self._tc_layers.get(scope)
         if t is None:
-            t = self._tc_layers[scope] = ops.Conv3x3TC(self.layers[scope])
+            t = self._tc_layers[scope] = ops.ConvTC(self.layers[scope])
         return t
 
-    def _trunk_tc(self, net, pre, blk, fin, terms):
-        cur = ops.f32_to_split(net)
+    @staticmethod
+    def _terms():
+        return 3 if TRUNK_MODE == "tc3" else 1
+
+    def _tc_usable(self, hh, ww):
+        """All tcgen05 layers tile 8x16 pixel blocks (16x32 input pixels for stride 2)."""
+        return TRUNK_MODE in ("tc3", "tc1") and hh >= 16 and ww >= 32
+
+    def _trunk_tc(self, cur, pre, blk, fin):
+        """cur: split-fp16 pair.  15 residual blocks + final block, 3 skip levels."""
+        terms = self._terms()
         r0 = cur
         for b in range(self.config.arch_param_B):
             rb = cur
             for i in (1, 2, 3):
                 sc = pre + blk % (b, b, i)
-                t = ops.conv3x3_tc(cur[0], cur[1], self._tc(sc + "/conv1"), terms=terms)
-                cur = ops.conv3x3_tc(t[0], t[1], self._tc(sc + "/conv2"), res1=cur, res2=rb if i == 3 else None,
-                                     terms=terms)
-        t = ops.conv3x3_tc(cur[0], cur[1], self._tc(pre + fin + "/conv1"), terms=terms)
-        cur = ops.conv3x3_tc(t[0], t[1], self._tc(pre + fin + "/conv2"), res1=cur, res2=r0, terms=terms)
-        return ops.split_to_f32(cur[0], cur[1])
+                t = ops.conv_tc(cur, self._tc(sc + "/conv1"), terms=terms)
+                cur = ops.conv_tc(t, self._tc(sc + "/conv2"), res1=cur, res2=rb if i == 3 else None, terms=terms)
+        t = ops.conv_tc(cur, self._tc(pre + fin + "/conv1"), terms=terms)
+        return ops.conv_tc(t, self._tc(pre + fin + "/conv2"), res1=cur, res2=r0, terms=terms)
 
+    def _encode_tc(self, x):
+        L, E, terms = self.layers, synth.ENC, self._terms()
+        net = ops.nchw_to_nhwc(x, normalize=True)
+        net = ops.conv2d(net, L[E + "h1"])  # cin = 3: CUDA cores (0.5 % of the FLOPs)
+        cur = ops.f32_to_split(net)
+        cur = ops.conv_tc(cur, self._tc(E + "h2"), terms=terms)
+        cur = self._trunk_tc(cur, E, "res_block_enc_%d/enc_%d_%d", "res_block_enc_final")
+        return ops.conv_tc(cur, self._tc(E + "to_bn"), terms=terms, out_f32=True)
+
+    def _decode_tc(self, q_nhwc):
+        D, terms = synth.DEC, self._terms()
+        cur = ops.f32_to_split(q_nhwc)
+        cur = ops.conv_tc(cur, self._tc(D + "from_bn"), terms=terms)
+        cur = self._trunk_tc(cur, D, "res_block_dec_%d/dec_%d_%d", "dec_after_res")
+        cur = ops.conv_tc(cur, self._tc(D + "h12"), terms=terms)
+        return ops.conv_tc(cur, self._tc(D + "h13"), terms=terms, out_f32=True)  # BN, denormalise, clip fused
+
+    # -- CUDA-core fp32 path (v1 kernels; on-GPU cross-check and small-image fallback) -------------
     def _trunk(self, net, pre, blk, fin):
-        if TRUNK_MODE in ("tc3", "tc1") and net.shape[1] >= 8 and net.shape[2] >= 16:
-            return self._trunk_tc(net, pre, blk, fin, 3 if TRUNK_MODE == "tc3" else 1)
         L = self.layers
         r0 = net
         for b in range(self.config.arch_param_B):
@@ -150,11 +173,14 @@ class _CVPR(_Network):
     def _encode(self, x):
         """x: (N,3,H,W) fp32 CUDA tensor, uint8-valued."""
         L, E = self.layers, synth.ENC
-        net = ops.nchw_to_nhwc(x, normalize=True)
-        net = ops.conv2d(net, L[E + "h1"])
-        net = ops.conv2d(net, L[E + "h2"])
-        net = self._trunk(net, E, "res_block_enc_%d/enc_%d_%d", "res_block_enc_final")
-        z33 = ops.conv2d(net, L[E + "to_bn"])
+        if self._tc_usable(x.shape[2] // 4, x.shape[3] // 4):
+            z33 = self._encode_tc(x)
+        else:
+            net = ops.nchw_to_nhwc(x, normalize=True)
+            net = ops.conv2d(net, L[E + "h1"])
+            net = ops.conv2d(net, L[E + "h2"])
+            net = self._trunk(net, E, "res_block_enc_%d/enc_%d_%d", "res_block_enc_final")
+            z33 = ops.conv2d(net, L[E + "to_bn"])
         qbar_nhwc, qbar_nchw, symbols = ops.heatmap_quantize(z33, self._centers)
         qbar_nchw._dsin_nhwc = qbar_nhwc
         return EncoderOutput(qbar_nchw, None, symbols, None, None)
@@ -165,10 +191,13 @@ class _CVPR(_Network):
         q_nhwc = getattr(q, "_dsin_nhwc", None)
         if q_nhwc is None:
             q_nhwc = ops.nchw_to_nhwc(q.contiguous(), normalize=False)
-        net = ops.conv2d(q_nhwc, L[D + "from_bn"])
-        net = self._trunk(net, D, "res_block_dec_%d/dec_%d_%d", "dec_after_res")
-        net = ops.conv2d(net, L[D + "h12"])
-        img_nhwc = ops.conv2d(net, L[D + "h13"])  # BN, denormalise, clip fused
+        if self._tc_usable(2 * q.shape[2], 2 * q.shape[3]):
+            img_nhwc = self._decode_tc(q_nhwc)
+        else:
+            net = ops.conv2d(q_nhwc, L[D + "from_bn"])
+            net = self._trunk(net, D, "res_block_dec_%d/dec_%d_%d", "dec_after_res")
+            net = ops.conv2d(net, L[D + "h12"])
+            img_nhwc = ops.conv2d(net, L[D + "h13"])  # BN, denormalise, clip fused
         out = ops.nhwc_to_nchw(img_nhwc)
         out._dsin_nhwc = img_nhwc
         return out

@@ -1,44 +1,57 @@
-// K1 on tensor cores: 3x3 stride-1 128->128 convolution as a tcgen05 implicit GEMM.
-//   replaces slim.conv2d + batch_norm + ReLU + skip adds of the 64 trunk layers
-//   (src/autoencoder_imgcomp.py:229-234,257-262,275-288).
+// K1/K2/K8 on tensor cores: convolution as a tcgen05 implicit GEMM, generic over
+//   kernel taps (3x3, 5x5, 1x1), dilation, stride 2 (TMA element strides) and stride-2 TRANSPOSED
+//   convolution (four sub-pixel phases, each a stride-1 conv over a subset of the taps),
+//   cin in {32, 64, 128}, cout <= 128.
+// Replaces slim.conv2d / conv2d_transpose + batch_norm + ReLU + skip adds
+// (src/autoencoder_imgcomp.py:223-266,275-288) and the SI-Net convs (src/siNet.py:31-40).
 //
-// GEMM view per output tile: D[128 pixels x 128 couts] = sum over 9 taps x 2 channel halves of
-//   A_tap[128 px x 64 ci] * B_tap[64 ci x 128 co].
-// A comes straight from the NHWC fp16 activation by a 4-D TMA box (64 ch, 16 w, 8 h, 1 n) whose
-// (w,h) origin is shifted by the tap; out-of-bounds box elements are zero-filled by TMA, which IS the
-// TF 'SAME' zero padding.  B is the per-tap [co][ci] weight slab (K-major).  Both land in shared
-// memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes; accumulators live in TMEM
-// (2 x 128 columns, double buffered) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// GEMM view per tile: D[128 grid pixels x NPAD couts] = sum over taps t, channel blocks c of
+//   A_{t,c}[128 px x KC ci] * B_{t,c}[KC ci x NPAD co].
+// A comes straight from the NHWC fp16 activation by a 4-D TMA box (KC ch, 16 w, 8 h, 1 n) whose
+// (w,h) origin is shifted by the tap offset; out-of-bounds elements are zero-filled by TMA, which IS
+// TF 'SAME' zero padding (and the implicit zeros of the transposed conv).  B is the per-tap [co][ci]
+// weight slab (K-major).  Both land in shared memory in the swizzled K-major layout tcgen05.mma
+// consumes; accumulators live in TMEM (double buffered) so the epilogue of tile i overlaps the MMAs of
+// tile i+1.
 //
-// Precision ("terms"): activations and weights are carried as split fp16 pairs (v = hi + lo).
+// Precision ("terms"): activations and weights are split fp16 pairs (v = hi + lo).
 //   terms = 3:  hi*hi + hi*lo + lo*hi  -> ~22-bit operands, fp32-class result (parity mode)
 //   terms = 1:  hi*hi only             -> fp16 operands (fast mode)
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
-// warps 2-5 = epilogue (TMEM -> registers -> scale/shift/act/residual -> split fp16 -> global).
+// warps 2-5 = epilogue (TMEM -> registers -> scale/shift/act/residual/post -> global).
 #include "tc_common.cuh"
 
 using namespace tc;
 
 namespace {
 
-constexpr int BW = 16, BH = 8;          // spatial tile: 8 rows x 16 cols = 128 GEMM rows
-constexpr int TILE_BYTES = 128 * 128;   // 128 rows x 64 fp16 = 16 KB
-constexpr int NUM_KB = 18;              // 9 taps x 2 halves of the 128 input channels
+constexpr int BW = 16, BH = 8;  // spatial tile: 8 rows x 16 cols = 128 GEMM rows
+constexpr int MAX_TAPS = 25;
 
-struct TcP {
+struct GP {
   const float* scale;
   const float* shift;
   const __half *r1h, *r1l, *r2h, *r2l;
   __half *yh, *yl;
-  int n, H, W, act;
+  float* yf;
+  int n, GH, GW, OH, OW, cout, os, py, px, in_step, act, post, ntaps, nchunks;
   int tiles_w, tiles_h, total_tiles;
+  short dy[MAX_TAPS], dx[MAX_TAPS], wi[MAX_TAPS];
 };
 
-template <int TERMS>
+constexpr int up1024(int v) { return (v + 1023) / 1024 * 1024; }
+
+template <int KC, int NPAD, int TERMS>
 struct Cfg {
-  static constexpr int kStages = TERMS == 3 ? 3 : 6;
-  static constexpr int kStageBytes = (TERMS == 3 ? 4 : 2) * TILE_BYTES;
-  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 2048 /*barriers, scale, shift*/;
+  static constexpr int kA = up1024(128 * KC * 2);
+  static constexpr int kB = up1024(NPAD * KC * 2);
+  static constexpr int kStage = (TERMS == 3 ? 2 : 1) * (kA + kB);
+  static constexpr int kStagesRaw = (196 * 1024) / kStage;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmem = kStages * kStage + 1024 + 2048;
+  static constexpr int kTmemCols = 2 * NPAD <= 32 ? 32 : (2 * NPAD <= 64 ? 64 : (2 * NPAD <= 128 ? 128 : 256));
+  static constexpr uint32_t kLayout = KC == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
+  static constexpr uint32_t kSbo = KC == 64 ? 1024 : 512;
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
@@ -51,12 +64,30 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   }
 }
 
-template <int TERMS>
+__device__ __forceinline__ void add_residual16(float* f, const __half* rh, const __half* rl, size_t off) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    float a[8], b[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(rh + off) + g), a);
+    if (rl) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(rl + off) + g), b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = __fadd_rn(a[e], b[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[g * 8 + e] = __fadd_rn(f[g * 8 + e], a[e]);
+  }
+}
+
+template <int KC, int NPAD, int TERMS>
 __global__ void __launch_bounds__(192, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
-                  const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl, TcP p) {
-  constexpr int S = Cfg<TERMS>::kStages;
-  constexpr int STAGE = Cfg<TERMS>::kStageBytes;
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
+               const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
+               const __grid_constant__ GP p) {
+  using C = Cfg<KC, NPAD, TERMS>;
+  constexpr int S = C::kStages;
+  constexpr int STAGE = C::kStage;
+  constexpr int OFF_B = C::kA, OFF_ALO = C::kA + C::kB, OFF_BLO = 2 * C::kA + C::kB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -88,14 +119,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
     }
   }
   for (int i = threadIdx.x; i < 128; i += blockDim.x) {
-    s_scale[i] = p.scale[i];
-    s_shift[i] = p.shift[i];
+    s_scale[i] = i < p.cout ? p.scale[i] : 0.f;
+    s_shift[i] = i < p.cout ? p.shift[i] : 0.f;
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, 256);
+  if (warp == 1) tmem_alloc(tmem_ptr, C::kTmemCols);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  const int num_kb = p.ntaps * p.nchunks;
+  constexpr uint32_t kBytes = (TERMS == 3 ? 2u : 1u) * (128u * KC * 2u + (uint32_t)NPAD * KC * 2u);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -105,18 +138,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int tw = tile % p.tiles_w, t2 = tile / p.tiles_w;
         const int th = t2 % p.tiles_h, n = t2 / p.tiles_h;
-        const int ox0 = tw * BW, oy0 = th * BH;
-        for (int kb = 0; kb < NUM_KB; ++kb) {
-          const int tap = kb >> 1, cc = kb & 1;
-          const int ky = tap / 3, kx = tap - 3 * ky;
+        const int x0 = tw * BW * p.in_step, y0 = th * BH * p.in_step;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / p.nchunks, cc = kb - tap * p.nchunks;
           mbar_wait(&empty[stage], phase ^ 1u);
           uint8_t* st = tiles + stage * STAGE;
-          mbar_expect_tx(&full[stage], STAGE);
-          tma_load_4d(st, &tm_xh, &full[stage], cc * 64, ox0 + kx - 1, oy0 + ky - 1, n);
-          tma_load_2d(st + TILE_BYTES, &tm_wh, &full[stage], cc * 64, tap * 128);
+          mbar_expect_tx(&full[stage], kBytes);
+          const int ax = x0 + p.dx[tap], ay = y0 + p.dy[tap], wrow = p.wi[tap] * NPAD;
+          tma_load_4d(st, &tm_xh, &full[stage], cc * KC, ax, ay, n);
+          tma_load_2d(st + OFF_B, &tm_wh, &full[stage], cc * KC, wrow);
           if (TERMS == 3) {
-            tma_load_4d(st + 2 * TILE_BYTES, &tm_xl, &full[stage], cc * 64, ox0 + kx - 1, oy0 + ky - 1, n);
-            tma_load_2d(st + 3 * TILE_BYTES, &tm_wl, &full[stage], cc * 64, tap * 128);
+            tma_load_4d(st + OFF_ALO, &tm_xl, &full[stage], cc * KC, ax, ay, n);
+            tma_load_2d(st + OFF_BLO, &tm_wl, &full[stage], cc * KC, wrow);
           }
           if (++stage == S) {
             stage = 0;
@@ -128,38 +161,37 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (single thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, 128, 0);
+      constexpr uint32_t idesc = make_idesc_f16(128, NPAD, 0);
       int stage = 0, it = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
-        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(&tempty[acc], aphase ^ 1u);
+        mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
-        for (int kb = 0; kb < NUM_KB; ++kb) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * NPAD;
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           fence_after_sync();
           const uint32_t sa = smem_u32(tiles + stage * STAGE);
-          const uint64_t a_hi = make_smem_desc(sa, 16, 1024, LAYOUT_SW128);
-          const uint64_t b_hi = make_smem_desc(sa + TILE_BYTES, 16, 1024, LAYOUT_SW128);
-          const uint64_t a_lo = make_smem_desc(sa + 2 * TILE_BYTES, 16, 1024, LAYOUT_SW128);
-          const uint64_t b_lo = make_smem_desc(sa + 3 * TILE_BYTES, 16, 1024, LAYOUT_SW128);
+          const uint64_t a_hi = make_smem_desc(sa, 16, C::kSbo, C::kLayout);
+          const uint64_t b_hi = make_smem_desc(sa + OFF_B, 16, C::kSbo, C::kLayout);
+          const uint64_t a_lo = make_smem_desc(sa + OFF_ALO, 16, C::kSbo, C::kLayout);
+          const uint64_t b_lo = make_smem_desc(sa + OFF_BLO, 16, C::kSbo, C::kLayout);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x K=16 per 64-channel block; +32 B per step
+          for (int k = 0; k < KC / 16; ++k) {  // +32 B per K=16 step inside the swizzled row
             umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) ? 1u : 0u);
             if (TERMS == 3) {
               umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
               umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
             }
           }
-          umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above retire
+          umma_commit(&empty[stage]);
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        umma_commit(&tfull[acc]);
       }
     }
   } else {
@@ -170,70 +202,61 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const int tw = tile % p.tiles_w, t2 = tile / p.tiles_w;
       const int th = t2 % p.tiles_h, n = t2 / p.tiles_h;
-      const int oy = th * BH + hl, ox = tw * BW + wl;
-      const bool valid = oy < p.H && ox < p.W;
-      const size_t pix = ((size_t)n * p.H + oy) * p.W + ox;
-      mbar_wait(&tfull[acc], aphase);
+      const int gy = th * BH + hl, gx = tw * BW + wl;
+      const int oy = gy * p.os + p.py, ox = gx * p.os + p.px;
+      const bool valid = gy < p.GH && gx < p.GW && oy < p.OH && ox < p.OW;
+      const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
+      mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u);
       fence_after_sync();
 #pragma unroll 1
-      for (int chunk = 0; chunk < 4; ++chunk) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + chunk * 32), v);
+      for (int chunk = 0; chunk < NPAD / 16; ++chunk) {
+        const int c0 = chunk * 16;
+        if (c0 >= p.cout) break;  // warp-uniform
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NPAD + c0), v);
         tmem_ld_wait();
         if (valid) {
-          float f[32];
+          float f[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = chunk * 32 + j;
-            float t = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), s_scale[c]), s_shift[c]);
-            f[j] = p.act == DSIN_ACT_RELU ? fmaxf(t, 0.f) : t;
+          for (int j = 0; j < 16; ++j) {
+            float t = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), s_scale[c0 + j]), s_shift[c0 + j]);
+            if (p.act == DSIN_ACT_RELU) t = fmaxf(t, 0.f);
+            else if (p.act == DSIN_ACT_LRELU02) t = fmaxf(__fmul_rn(t, 0.2f), t);
+            f[j] = t;
           }
-          const size_t off = pix * 128 + chunk * 32;
-          if (p.r1h) {
+          const size_t off = pix * p.cout + c0;
+          if (p.r1h) add_residual16(f, p.r1h, p.r1l, off);
+          if (p.r2h) add_residual16(f, p.r2h, p.r2l, off);
+          if (p.post != DSIN_POST_NONE) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float a[8], b[8];
-              unpack8(__ldg(reinterpret_cast<const uint4*>(p.r1h + off) + g), a);
-              if (p.r1l) {
-                unpack8(__ldg(reinterpret_cast<const uint4*>(p.r1l + off) + g), b);
+            for (int j = 0; j < 3; ++j) {
+              float t = __fadd_rn(__fmul_rn(f[j], dsin_std(j)), dsin_mean(j));
+              f[j] = p.post == DSIN_POST_DENORM_CLIP ? fminf(fmaxf(t, 0.f), 255.f) : t;
+            }
+          }
+          if (p.yf) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) a[e] = __fadd_rn(a[e], b[e]);
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.cout) p.yf[off + j] = f[j];
+          } else {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              uint4 uh, ul;
+              __half2* hh = reinterpret_cast<__half2*>(&uh);
+              __half2* ll = reinterpret_cast<__half2*>(&ul);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x0 = f[g * 8 + 2 * e], x1 = f[g * 8 + 2 * e + 1];
+                __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                hh[e] = __halves2half2(h0, h1);
+                ll[e] = __halves2half2(__float2half_rn(x0 - __half2float(h0)),
+                                       __float2half_rn(x1 - __half2float(h1)));
               }
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[g * 8 + e] = __fadd_rn(f[g * 8 + e], a[e]);
+              reinterpret_cast<uint4*>(p.yh + off)[g] = uh;
+              if (p.yl) reinterpret_cast<uint4*>(p.yl + off)[g] = ul;
             }
-          }
-          if (p.r2h) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float a[8], b[8];
-              unpack8(__ldg(reinterpret_cast<const uint4*>(p.r2h + off) + g), a);
-              if (p.r2l) {
-                unpack8(__ldg(reinterpret_cast<const uint4*>(p.r2l + off) + g), b);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) a[e] = __fadd_rn(a[e], b[e]);
-              }
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[g * 8 + e] = __fadd_rn(f[g * 8 + e], a[e]);
-            }
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 uh, ul;
-            __half2* hh = reinterpret_cast<__half2*>(&uh);
-            __half2* ll = reinterpret_cast<__half2*>(&ul);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float x0 = f[g * 8 + 2 * e], x1 = f[g * 8 + 2 * e + 1];
-              __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-              hh[e] = __halves2half2(h0, h1);
-              ll[e] = __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
-            }
-            reinterpret_cast<uint4*>(p.yh + off)[g] = uh;
-            if (p.yl) reinterpret_cast<uint4*>(p.yl + off)[g] = ul;
           }
         }
       }
@@ -246,18 +269,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     fence_after_sync();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
-// weights [3][3][cin][cout] fp32 -> [tap][cout][cin] split fp16 with a per-cout power-of-two scale that
+// weights [taps][cin][cout] fp32 -> [tap][npad][cin] split fp16 with a per-cout power-of-two scale that
 // moves the row's largest |w| into [8,16) so that the lo part stays in fp16's normal range.
-__global__ void pack_w3x3_kernel(const float* __restrict__ w, __half* __restrict__ w_hi, __half* __restrict__ w_lo,
-                                 float* __restrict__ wscale, int cin, int cout) {
-  const int co = blockIdx.x;
+__global__ void pack_w_tc_kernel(const float* __restrict__ w, __half* __restrict__ w_hi, __half* __restrict__ w_lo,
+                                 float* __restrict__ wscale, int taps, int cin, int cout, int npad) {
+  const int co = blockIdx.x;  // 0..npad-1
   __shared__ float s_max[128];
   float m = 0.f;
-  for (int i = threadIdx.x; i < 9 * cin; i += blockDim.x) m = fmaxf(m, fabsf(w[(size_t)i * cout + co]));
+  if (co < cout)
+    for (int i = threadIdx.x; i < taps * cin; i += blockDim.x) m = fmaxf(m, fabsf(w[(size_t)i * cout + co]));
   s_max[threadIdx.x] = m;
   __syncthreads();
   for (int s = 64; s > 0; s >>= 1) {
@@ -268,44 +292,163 @@ __global__ void pack_w3x3_kernel(const float* __restrict__ w, __half* __restrict
   int ex = 0;
   float sc = 1.f;
   if (m > 0.f) {
-    frexpf(m, &ex);           // m = f * 2^ex, f in [0.5,1)
-    sc = ldexpf(1.f, 4 - ex); // m*sc in [8,16)
+    frexpf(m, &ex);            // m = f * 2^ex, f in [0.5,1)
+    sc = ldexpf(1.f, 4 - ex);  // m*sc in [8,16)
   }
-  if (threadIdx.x == 0) wscale[co] = sc;
-  for (int i = threadIdx.x; i < 9 * cin; i += blockDim.x) {
+  if (threadIdx.x == 0 && co < cout) wscale[co] = sc;
+  for (int i = threadIdx.x; i < taps * cin; i += blockDim.x) {
     int tap = i / cin, ci = i - tap * cin;
-    float v = w[(size_t)i * cout + co] * sc;
+    float v = co < cout ? w[(size_t)i * cout + co] * sc : 0.f;
     __half hi = __float2half_rn(v);
-    size_t o = ((size_t)tap * cout + co) * cin + ci;
+    size_t o = ((size_t)tap * npad + co) * cin + ci;
     w_hi[o] = hi;
     w_lo[o] = __float2half_rn(v - __half2float(hi));
   }
 }
 
-template <int TERMS>
-int launch_tc(dsin_handle_t h, const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh,
-              const CUtensorMap& wl, const TcP& p, cudaStream_t st) {
+template <int KC, int NPAD, int TERMS>
+int launch_one(dsin_handle_t h, const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh,
+               const CUtensorMap& wl, const GP& p, cudaStream_t st) {
+  using C = Cfg<KC, NPAD, TERMS>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(conv3x3_tc_kernel<TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             Cfg<TERMS>::kSmem) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_tc_kernel<KC, NPAD, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             C::kSmem) != cudaSuccess)
       return dsin_fail(h, DSIN_ERR_CUDA, "%s: cannot raise dynamic shared memory", __func__);
     configured = true;
   }
   int grid = p.total_tiles < h->sm_count ? p.total_tiles : h->sm_count;
-  conv3x3_tc_kernel<TERMS><<<grid, 192, Cfg<TERMS>::kSmem, st>>>(xh, xl, wh, wl, p);
+  conv_tc_kernel<KC, NPAD, TERMS><<<grid, 192, C::kSmem, st>>>(xh, xl, wh, wl, p);
   DSIN_LAUNCHED(h);
   return DSIN_OK;
 }
 
+template <int KC, int NPAD>
+int launch_terms(dsin_handle_t h, int terms, const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh,
+                 const CUtensorMap& wl, const GP& p, cudaStream_t st) {
+  return terms == 3 ? launch_one<KC, NPAD, 3>(h, xh, xl, wh, wl, p, st)
+                    : launch_one<KC, NPAD, 1>(h, xh, xl, wh, wl, p, st);
+}
+
+int npad_of(int cout) { return (cout + 15) / 16 * 16; }
+int kc_of(int cin) { return cin % 64 == 0 ? 64 : 32; }
+
 }  // namespace
+
+extern "C" int dsin_conv_tc_npad(int cout) { return npad_of(cout); }
+
+extern "C" int dsin_pack_conv_w_tc(dsin_handle_t h, const float* w_kkio, int taps, int cin, int cout,
+                                   uint16_t* w_hi, uint16_t* w_lo, float* wscale, void* stream) {
+  DSIN_REQUIRE(h, w_kkio && w_hi && w_lo && wscale, "null pointer");
+  DSIN_REQUIRE(h, taps >= 1 && taps <= MAX_TAPS && cin % 32 == 0 && cin <= 128 && cout >= 1 && cout <= 128,
+               "unsupported shape");
+  const int npad = npad_of(cout);
+  pack_w_tc_kernel<<<npad, 128, 0, (cudaStream_t)stream>>>(w_kkio, (__half*)w_hi, (__half*)w_lo, wscale, taps, cin,
+                                                          cout, npad);
+  DSIN_LAUNCHED(h);
+  return DSIN_OK;
+}
 
 extern "C" int dsin_pack_conv3x3_w(dsin_handle_t h, const float* w_hwio, uint16_t* w_hi, uint16_t* w_lo,
                                    float* wscale, int cin, int cout, void* stream) {
-  DSIN_REQUIRE(h, w_hwio && w_hi && w_lo && wscale, "null pointer");
-  DSIN_REQUIRE(h, cin == 128 && cout == 128, "only 128 -> 128 channels are built");
-  pack_w3x3_kernel<<<cout, 128, 0, (cudaStream_t)stream>>>(w_hwio, (__half*)w_hi, (__half*)w_lo, wscale, cin, cout);
-  DSIN_LAUNCHED(h);
+  DSIN_REQUIRE(h, cin == 128 && cout == 128, "only 128 -> 128 channels");
+  return dsin_pack_conv_w_tc(h, w_hwio, 9, cin, cout, w_hi, w_lo, wscale, stream);
+}
+
+extern "C" int dsin_conv2d_tc(dsin_handle_t h, const dsin_conv_desc_t* d, int terms, const uint16_t* x_hi,
+                              const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo,
+                              const float* scale, const float* shift, const uint16_t* res1_hi,
+                              const uint16_t* res1_lo, const uint16_t* res2_hi, const uint16_t* res2_lo,
+                              uint16_t* y_hi, uint16_t* y_lo, float* y_f32, void* stream) {
+  DSIN_REQUIRE(h, d && x_hi && w_hi && scale && shift && (y_hi || y_f32), "null pointer");
+  DSIN_REQUIRE(h, terms == 1 || terms == 3, "terms must be 1 or 3");
+  DSIN_REQUIRE(h, terms == 1 || (x_lo && w_lo), "terms == 3 needs the lo planes");
+  DSIN_REQUIRE(h, d->cin % 32 == 0 && d->cin <= 128 && d->cout >= 1 && d->cout <= 128, "unsupported channels");
+  DSIN_REQUIRE(h, d->kh == d->kw && d->kh * d->kw <= MAX_TAPS, "unsupported kernel size");
+  DSIN_REQUIRE(h, d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
+  DSIN_REQUIRE(h, !d->transposed || d->stride == 2, "transposed conv is stride 2");
+  DSIN_REQUIRE(h, y_f32 || d->cout % 16 == 0, "split-fp16 output needs cout % 16 == 0");
+  DSIN_REQUIRE(h, d->post == DSIN_POST_NONE || d->cout == 3, "denormalisation needs cout == 3");
+  const int k = d->kh, KC = kc_of(d->cin), NPAD = npad_of(d->cout);
+  const int step = (!d->transposed && d->stride == 2) ? 2 : 1;
+  DSIN_REQUIRE(h, d->h >= BH * step && d->w >= BW * step, "image smaller than one tile");
+
+  CUtensorMap xh, xl, wh, wl;
+  const uint64_t xd[4] = {(uint64_t)d->cin, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
+  const uint64_t xs[3] = {(uint64_t)d->cin * 2, (uint64_t)d->w * d->cin * 2, (uint64_t)d->h * d->w * d->cin * 2};
+  const uint32_t xb[4] = {(uint32_t)KC, (uint32_t)(BW * step), (uint32_t)(BH * step), 1};
+  const uint32_t xe[4] = {1, (uint32_t)step, (uint32_t)step, 1};
+  const uint64_t wd[2] = {(uint64_t)d->cin, (uint64_t)k * k * NPAD};
+  const uint64_t wsb[1] = {(uint64_t)d->cin * 2};
+  const uint32_t wb[2] = {(uint32_t)KC, (uint32_t)NPAD};
+  const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  bool ok = encode_tmap(&xh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x_hi, xd, xs, xb, sw, xe) &&
+            encode_tmap(&xl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x_lo ? x_lo : x_hi, xd, xs, xb, sw, xe) &&
+            encode_tmap(&wh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w_hi, wd, wsb, wb, sw) &&
+            encode_tmap(&wl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w_lo ? w_lo : w_hi, wd, wsb, wb, sw);
+  if (!ok) return dsin_fail(h, DSIN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", __func__);
+
+  GP p;
+  memset(&p, 0, sizeof(p));
+  p.scale = scale; p.shift = shift;
+  p.r1h = (const __half*)res1_hi; p.r1l = (const __half*)res1_lo;
+  p.r2h = (const __half*)res2_hi; p.r2l = (const __half*)res2_lo;
+  p.yh = (__half*)y_hi; p.yl = (__half*)y_lo; p.yf = y_f32;
+  p.n = d->n; p.cout = d->cout; p.act = d->act; p.post = d->post;
+  p.nchunks = d->cin / KC;
+  p.in_step = step;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  auto launch = [&](const GP& gp) -> int {
+    if (KC == 64 && NPAD == 128) return launch_terms<64, 128>(h, terms, xh, xl, wh, wl, gp, st);
+    if (KC == 64 && NPAD == 64) return launch_terms<64, 64>(h, terms, xh, xl, wh, wl, gp, st);
+    if (KC == 64 && NPAD == 48) return launch_terms<64, 48>(h, terms, xh, xl, wh, wl, gp, st);
+    if (KC == 64 && NPAD == 16) return launch_terms<64, 16>(h, terms, xh, xl, wh, wl, gp, st);
+    if (KC == 32 && NPAD == 128) return launch_terms<32, 128>(h, terms, xh, xl, wh, wl, gp, st);
+    if (KC == 32 && NPAD == 32) return launch_terms<32, 32>(h, terms, xh, xl, wh, wl, gp, st);
+    if (KC == 32 && NPAD == 16) return launch_terms<32, 16>(h, terms, xh, xl, wh, wl, gp, st);
+    return dsin_fail(h, DSIN_ERR_UNSUPPORTED, "%s: no tensor-core instantiation for this (cin, cout)", __func__);
+  };
+
+  if (!d->transposed) {
+    p.OH = (d->h + d->stride - 1) / d->stride; p.OW = (d->w + d->stride - 1) / d->stride;
+    p.GH = p.OH; p.GW = p.OW; p.os = 1; p.py = 0; p.px = 0;
+    const int pt = dsin_same_pad_before(d->h, k, d->stride, d->dilation);
+    const int pl = dsin_same_pad_before(d->w, k, d->stride, d->dilation);
+    p.ntaps = k * k;
+    for (int ky = 0; ky < k; ++ky)
+      for (int kx = 0; kx < k; ++kx) {
+        p.dy[ky * k + kx] = (short)(ky * d->dilation - pt);
+        p.dx[ky * k + kx] = (short)(kx * d->dilation - pl);
+        p.wi[ky * k + kx] = (short)(ky * k + kx);
+      }
+    p.tiles_w = (p.GW + BW - 1) / BW; p.tiles_h = (p.GH + BH - 1) / BH;
+    p.total_tiles = d->n * p.tiles_w * p.tiles_h;
+    return launch(p);
+  }
+  // stride-2 transposed conv, TF SAME: out[o] = sum_{i,k: 2i + k - b = o} in[i] w[k]; phase (py,px) of the
+  // output is a stride-1 conv over the input grid with the taps of matching parity.
+  p.OH = 2 * d->h; p.OW = 2 * d->w; p.GH = d->h; p.GW = d->w; p.os = 2;
+  const int bt = dsin_same_pad_before(p.OH, k, 2, 1), bl = dsin_same_pad_before(p.OW, k, 2, 1);
+  p.tiles_w = (p.GW + BW - 1) / BW; p.tiles_h = (p.GH + BH - 1) / BH;
+  p.total_tiles = d->n * p.tiles_w * p.tiles_h;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      GP gp = p;
+      gp.py = py; gp.px = px; gp.ntaps = 0;
+      for (int ky = 0; ky < k; ++ky) {
+        if ((py + bt - ky) & 1) continue;
+        for (int kx = 0; kx < k; ++kx) {
+          if ((px + bl - kx) & 1) continue;
+          gp.dy[gp.ntaps] = (short)((py + bt - ky) / 2);
+          gp.dx[gp.ntaps] = (short)((px + bl - kx) / 2);
+          gp.wi[gp.ntaps] = (short)(ky * k + kx);
+          gp.ntaps++;
+        }
+      }
+      int rc = launch(gp);
+      if (rc != DSIN_OK) return rc;
+    }
   return DSIN_OK;
 }
 
@@ -314,33 +457,8 @@ extern "C" int dsin_conv3x3_c128_tc(dsin_handle_t h, int n, int hh, int ww, cons
                                     const float* scale, const float* shift, int act, const uint16_t* res1_hi,
                                     const uint16_t* res1_lo, const uint16_t* res2_hi, const uint16_t* res2_lo,
                                     uint16_t* y_hi, uint16_t* y_lo, int terms, void* stream) {
-  DSIN_REQUIRE(h, x_hi && w_hi && scale && shift && y_hi, "null pointer");
-  DSIN_REQUIRE(h, terms == 1 || terms == 3, "terms must be 1 or 3");
-  DSIN_REQUIRE(h, terms == 1 || (x_lo && w_lo && y_lo), "terms == 3 needs the lo planes");
-  DSIN_REQUIRE(h, n > 0 && hh >= BH && ww >= BW, "image smaller than one 8x16 tile");
-  DSIN_REQUIRE(h, act == DSIN_ACT_NONE || act == DSIN_ACT_RELU, "activation must be none or relu");
-  CUtensorMap xh, xl, wh, wl;
-  const uint64_t xd[4] = {128, (uint64_t)ww, (uint64_t)hh, (uint64_t)n};
-  const uint64_t xs[3] = {256, (uint64_t)ww * 256, (uint64_t)hh * ww * 256};
-  const uint32_t xb[4] = {64, BW, BH, 1};
-  const uint64_t wd[2] = {128, 9 * 128};
-  const uint64_t wsb[1] = {256};
-  const uint32_t wb[2] = {64, 128};
-  bool ok = encode_tmap(&xh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x_hi, xd, xs, xb, CU_TENSOR_MAP_SWIZZLE_128B) &&
-            encode_tmap(&xl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x_lo ? x_lo : x_hi, xd, xs, xb,
-                        CU_TENSOR_MAP_SWIZZLE_128B) &&
-            encode_tmap(&wh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w_hi, wd, wsb, wb, CU_TENSOR_MAP_SWIZZLE_128B) &&
-            encode_tmap(&wl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w_lo ? w_lo : w_hi, wd, wsb, wb,
-                        CU_TENSOR_MAP_SWIZZLE_128B);
-  if (!ok) return dsin_fail(h, DSIN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", __func__);
-  TcP p;
-  p.scale = scale; p.shift = shift;
-  p.r1h = (const __half*)res1_hi; p.r1l = (const __half*)res1_lo;
-  p.r2h = (const __half*)res2_hi; p.r2l = (const __half*)res2_lo;
-  p.yh = (__half*)y_hi; p.yl = (__half*)y_lo;
-  p.n = n; p.H = hh; p.W = ww; p.act = act;
-  p.tiles_w = (ww + BW - 1) / BW; p.tiles_h = (hh + BH - 1) / BH;
-  p.total_tiles = n * p.tiles_w * p.tiles_h;
-  cudaStream_t st = (cudaStream_t)stream;
-  return terms == 3 ? launch_tc<3>(h, xh, xl, wh, wl, p, st) : launch_tc<1>(h, xh, xl, wh, wl, p, st);
+  dsin_conv_desc_t d = {n, hh, ww, 128, 128, 3, 3, 1, 1, 0, act, DSIN_POST_NONE};
+  DSIN_REQUIRE(h, y_hi && (terms == 1 || y_lo), "null output");
+  return dsin_conv2d_tc(h, &d, terms, x_hi, x_lo, w_hi, w_lo, scale, shift, res1_hi, res1_lo, res2_hi, res2_lo, y_hi,
+                        y_lo, nullptr, stream);
 }

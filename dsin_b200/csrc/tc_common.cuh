@@ -111,6 +111,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ descriptors
@@ -118,7 +127,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // apart (SBO), tile base 1024-B aligned; advancing K by 16 elements = +32 B on the start address.
 // SWIZZLE_NONE ("interleave"): core matrix = 8 rows x 16 B with 16-B row pitch; lbo = byte distance
 // between the two 16-B K chunks of one MMA, sbo = byte distance between 8-row groups.
-enum { LAYOUT_NONE = 0, LAYOUT_SW128 = 2 };
+enum { LAYOUT_NONE = 0, LAYOUT_SW128 = 2, LAYOUT_SW64 = 4 };
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint32_t layout) {
   uint64_t d = 0;
@@ -154,7 +163,8 @@ static inline EncodeTiledFn get_encode_fn() {
 
 // dims/box: innermost first; strides_bytes: for dims 1..rank-1.  Returns false on failure.
 static inline bool encode_tmap(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
-                               const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw) {
+                               const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw,
+                               const uint32_t* elem_strides = nullptr) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t gd[5], gs[4];
@@ -162,7 +172,7 @@ static inline bool encode_tmap(CUtensorMap* m, CUtensorMapDataType dt, int rank,
   for (int i = 0; i < rank; ++i) {
     gd[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   return fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,

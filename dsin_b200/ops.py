@@ -172,41 +172,67 @@ def split_to_f32(hi, lo):
     return y
 
 
-class Conv3x3TC(object):
-    """Tensor-core form of a 3x3 128->128 ConvLayer: weights packed [tap][cout][cin] as split fp16 with a
-    per-cout power-of-two scale that is folded back into the epilogue scale (exact)."""
+class ConvTC(object):
+    """Tensor-core form of a ConvLayer (cin in {32,64,128}, cout <= 128): weights packed
+    [tap][npad][cin] as split fp16 with a per-cout power-of-two scale that is folded back into the
+    epilogue scale (exact)."""
 
     def __init__(self, layer):
-        assert (layer.kh, layer.kw, layer.cin, layer.cout) == (3, 3, 128, 128) and layer.stride == 1
-        assert layer.dilation == 1 and not layer.transposed
+        assert layer.cin % 32 == 0 and layer.cin <= 128 and layer.cout <= 128, (layer.cin, layer.cout)
         h = handle()
         dev = layer.w.device
-        self.w_hi = torch.empty((9, 128, 128), dtype=torch.float16, device=dev)
-        self.w_lo = torch.empty((9, 128, 128), dtype=torch.float16, device=dev)
-        wscale = torch.empty((128,), dtype=torch.float32, device=dev)
-        h.check(h.lib.dsin_pack_conv3x3_w(h.ptr, _p(layer.w), _p(self.w_hi), _p(self.w_lo), _p(wscale), 128, 128,
-                                          _stream()))
-        self.scale = (layer.scale / wscale).contiguous()  # power-of-two division: exact
-        self.shift = layer.shift
+        self.layer = layer
+        taps = layer.kh * layer.kw
+        npad = int(h.lib.dsin_conv_tc_npad(layer.cout))
+        self.w_hi = torch.empty((taps, npad, layer.cin), dtype=torch.float16, device=dev)
+        self.w_lo = torch.empty((taps, npad, layer.cin), dtype=torch.float16, device=dev)
+        wscale = torch.empty((layer.cout,), dtype=torch.float32, device=dev)
+        h.check(h.lib.dsin_pack_conv_w_tc(h.ptr, _p(layer.w), taps, layer.cin, layer.cout, _p(self.w_hi),
+                                          _p(self.w_lo), _p(wscale), _stream()))
+        base = layer.scale if layer.scale is not None else torch.ones_like(wscale)
+        self.scale = (base / wscale).contiguous()  # power-of-two division: exact
+        self.shift = layer.shift if layer.shift is not None else torch.zeros_like(wscale)
         self.act = layer.act
 
 
-def conv3x3_tc(xh, xl, tcl, res1=None, res2=None, terms=3):
-    """Split-fp16 NHWC in/out; res1/res2 are (hi, lo) pairs or None."""
+Conv3x3TC = ConvTC
+
+
+def conv_tc(x, tcl, res1=None, res2=None, terms=3, out_f32=False, post=None):
+    """x: (hi, lo) split-fp16 NHWC pair.  Returns a split pair, or an fp32 NHWC tensor if out_f32."""
     h = handle()
+    xh, xl = x
+    L = tcl.layer
     n, hh, ww, c = xh.shape
-    assert c == 128
-    yh = torch.empty_like(xh)
-    yl = torch.empty_like(xh)
+    assert c == L.cin
+    oh, ow = L.out_hw(hh, ww)
+    dev = xh.device
+    if out_f32:
+        yf = torch.empty((n, oh, ow, L.cout), dtype=torch.float32, device=dev)
+        yh = yl = None
+    else:
+        yf = None
+        yh = torch.empty((n, oh, ow, L.cout), dtype=torch.float16, device=dev)
+        yl = torch.empty((n, oh, ow, L.cout), dtype=torch.float16, device=dev)
     r1h, r1l = res1 if res1 is not None else (None, None)
     r2h, r2l = res2 if res2 is not None else (None, None)
+    d = ConvDesc(n, hh, ww, c, L.cout, L.kh, L.kw, L.stride, L.dilation, int(L.transposed), tcl.act,
+                 L.post if post is None else post)
     e0 = PROF.begin()
-    h.check(h.lib.dsin_conv3x3_c128_tc(h.ptr, n, hh, ww, _p(_chk(xh, torch.float16)), _p(xl), _p(tcl.w_hi),
-                                       _p(tcl.w_lo), _p(tcl.scale), _p(tcl.shift), tcl.act, _p(r1h), _p(r1l),
-                                       _p(r2h), _p(r2l), _p(yh), _p(yl), terms, _stream()))
+    h.check(h.lib.dsin_conv2d_tc(h.ptr, C.byref(d), terms, _p(_chk(xh, torch.float16)), _p(xl), _p(tcl.w_hi),
+                                 _p(tcl.w_lo), _p(tcl.scale), _p(tcl.shift), _p(r1h), _p(r1l), _p(r2h), _p(r2l),
+                                 _p(yh), _p(yl), _p(yf), _stream()))
     if e0 is not None:
-        PROF.end(e0, "conv3x3_128to128_tc%d" % terms, 2.0 * n * hh * ww * 9 * 128 * 128)
-    return yh, yl
+        pix = n * (hh * ww if L.transposed else oh * ow)
+        PROF.end(e0, "tc%d_conv%dx%d_%dto%d%s%s" % (terms, L.kh, L.kw, c, L.cout,
+                                                     "_T" if L.transposed else ("_s%d" % L.stride),
+                                                     "_d" if L.dilation > 1 else ""),
+                 2.0 * pix * L.kh * L.kw * c * L.cout)
+    return yf if out_f32 else (yh, yl)
+
+
+def conv3x3_tc(xh, xl, tcl, res1=None, res2=None, terms=3):
+    return conv_tc((xh, xl), tcl, res1=res1, res2=res2, terms=terms)
 
 
 def heatmap_quantize(z33_nhwc, centers):

@@ -12,11 +12,16 @@ import numpy as np
 from . import ops, synth
 
 
+# "tc3": tcgen05 split-fp16 (fp32-class); "tc1": tcgen05 fp16; "simt": CUDA-core fp32
+MODE = "tc3"
+
+
 class SiNet(object):
     RATES = (1, 2, 4, 8, 16, 32, 64, 128, 1)
 
     def __init__(self):
         self.layers = None
+        self._tc = None
         self.device = "cuda"
 
     def load_weights(self, W):
@@ -30,8 +35,18 @@ class SiNet(object):
         layers.append(ops.ConvLayer(W[sc + "/weights"], None, W[sc + "/biases"], act=ops.ACT_NONE,
                                     device=self.device))
         self.layers = layers
+        self._tc = None
 
     def _run(self, net, post):
+        n, hh, ww, _ = net.shape
+        if MODE in ("tc3", "tc1") and hh >= 8 and ww >= 16:
+            terms = 3 if MODE == "tc3" else 1
+            if self._tc is None:
+                self._tc = [ops.ConvTC(layer) for layer in self.layers[1:]]
+            cur = ops.f32_to_split(ops.conv2d(net, self.layers[0]))  # g_conv1 has cin = 6: CUDA cores
+            for tcl in self._tc[:-1]:
+                cur = ops.conv_tc(cur, tcl, terms=terms)
+            return ops.conv_tc(cur, self._tc[-1], terms=terms, out_f32=True, post=post)
         for layer in self.layers[:-1]:
             net = ops.conv2d(net, layer)
         return ops.conv2d(net, self.layers[-1], post=post)

@@ -80,6 +80,22 @@ int dsin_conv3x3_c128_tc(dsin_handle_t h, int n, int hh, int ww, const uint16_t*
                          const uint16_t* res1_hi, const uint16_t* res1_lo,
                          const uint16_t* res2_hi, const uint16_t* res2_lo, uint16_t* y_hi,
                          uint16_t* y_lo, int terms, void* stream);
+/* Generic tensor-core convolution (tcgen05): any layer of dsin_conv2d with cin in {32,64,128} and
+ * cout <= 128 -- stride 1 (any dilation), stride 2 (TMA element strides) and stride-2 transposed
+ * (four sub-pixel phases).  Same arithmetic/epilogue as dsin_conv2d; replaces the same reference
+ * lines (src/autoencoder_imgcomp.py:223-266, src/siNet.py:31-40).
+ * x_hi/x_lo, res*: split-fp16 NHWC planes; output either split fp16 (y_hi,y_lo; cout % 16 == 0) or
+ * fp32 NHWC (y_f32 != NULL).  Weights packed by dsin_pack_conv_w_tc from [taps][cin][cout] fp32 into
+ * [tap][npad][cin] split fp16 (npad = dsin_conv_tc_npad(cout)); wscale[cout] are the per-cout
+ * power-of-two factors the caller divides out of `scale`. */
+int dsin_conv_tc_npad(int cout);
+int dsin_pack_conv_w_tc(dsin_handle_t h, const float* w_kkio, int taps, int cin, int cout, uint16_t* w_hi,
+                        uint16_t* w_lo, float* wscale, void* stream);
+int dsin_conv2d_tc(dsin_handle_t h, const dsin_conv_desc_t* d, int terms, const uint16_t* x_hi,
+                   const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo, const float* scale,
+                   const float* shift, const uint16_t* res1_hi, const uint16_t* res1_lo,
+                   const uint16_t* res2_hi, const uint16_t* res2_lo, uint16_t* y_hi, uint16_t* y_lo,
+                   float* y_f32, void* stream);
 /* fp32 NHWC <-> split fp16 planes. */
 int dsin_f32_to_split(dsin_handle_t h, const float* x, uint16_t* hi, uint16_t* lo, int64_t count,
                       void* stream);

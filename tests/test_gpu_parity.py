@@ -304,3 +304,60 @@ def test_conv3x3_tc_matches_fp32_conv(terms, tol, shape):
     ref = ref + r1q + r2q
     err = float((got - ref).abs().max())
     assert err < tol * max(1.0, float(ref.abs().max())), err
+
+
+@pytest.mark.parametrize("terms,tol", [(3, 2e-5), (1, 4e-3)])  # 2e-5: fp32 tensor-core accumulation up to K=3200
+@pytest.mark.parametrize("case", [
+    dict(name="h2", k=5, cin=64, cout=128, stride=2, dil=1, tr=False, h=40, w=72, act=1, post=0, f32=False),
+    dict(name="to_bn", k=5, cin=128, cout=33, stride=2, dil=1, tr=False, h=20, w=36, act=0, post=0, f32=True),
+    dict(name="from_bn", k=3, cin=32, cout=128, stride=2, dil=1, tr=True, h=10, w=18, act=1, post=0, f32=False),
+    dict(name="h12", k=5, cin=128, cout=64, stride=2, dil=1, tr=True, h=20, w=36, act=1, post=0, f32=False),
+    dict(name="h13", k=5, cin=64, cout=3, stride=2, dil=1, tr=True, h=40, w=72, act=0, post=1, f32=True),
+    dict(name="sinet_d1", k=3, cin=32, cout=32, stride=1, dil=1, tr=False, h=40, w=48, act=2, post=0, f32=False),
+    dict(name="sinet_d16", k=3, cin=32, cout=32, stride=1, dil=16, tr=False, h=40, w=48, act=2, post=0, f32=False),
+    dict(name="sinet_d128", k=3, cin=32, cout=32, stride=1, dil=128, tr=False, h=40, w=48, act=2, post=0, f32=False),
+    dict(name="sinet_last", k=1, cin=32, cout=3, stride=1, dil=1, tr=False, h=24, w=40, act=0, post=2, f32=True),
+], ids=lambda c: c["name"])
+def test_generic_conv_tc_matches_float64(case, terms, tol):
+    """Every layer shape that runs on the generic tcgen05 conv vs a float64 reference computed from the
+    split-rounded values the kernel actually consumed."""
+    from dsin_b200 import ops
+    rng = np.random.default_rng(11)
+    k, cin, cout = case["k"], case["cin"], case["cout"]
+    x = rng.standard_normal((2, cin, case["h"], case["w"])).astype(np.float32)
+    if case["tr"]:
+        w_ref = (rng.standard_normal((k, k, cout, cin)) / np.sqrt(k * k * cin / 4)).astype(np.float32)
+        w_pack = np.transpose(w_ref, (0, 1, 3, 2))
+    else:
+        w_ref = (rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
+        w_pack = w_ref
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = (0.3 * rng.standard_normal(cout)).astype(np.float32)
+    layer = ops.ConvLayer(w_pack, scale, shift, stride=case["stride"], dilation=case["dil"], transposed=case["tr"],
+                          act=case["act"], post=case["post"])
+    tcl = ops.ConvTC(layer)
+    xs = ops.f32_to_split(_nhwc(_dev(x)))
+    xq = ops.split_to_f32(*xs).permute(0, 3, 1, 2).cpu().double()
+    if case["tr"]:
+        ref = O.conv2d_transpose_same_s2(xq, w_ref.astype(np.float64))
+    else:
+        ref = O.conv2d_same(xq, w_ref.astype(np.float64), stride=case["stride"], dilation=case["dil"])
+    ref = ref * torch.tensor(scale).double().view(1, -1, 1, 1) + torch.tensor(shift).double().view(1, -1, 1, 1)
+    if case["act"] == 1:
+        ref = torch.relu(ref)
+    elif case["act"] == 2:
+        ref = torch.maximum(0.2 * ref, ref)
+    res = None
+    if not case["f32"]:
+        r = rng.standard_normal(tuple(ref.shape)).astype(np.float32)
+        res = ops.f32_to_split(_nhwc(_dev(r)))
+        ref = ref + ops.split_to_f32(*res).permute(0, 3, 1, 2).cpu().double()
+    if case["post"]:
+        ref = O.denormalize(ref)
+        if case["post"] == 1:
+            ref = torch.clamp(ref, 0.0, 255.0)
+    out = ops.conv_tc(xs, tcl, res1=res, terms=terms, out_f32=case["f32"])
+    got = (out if case["f32"] else ops.split_to_f32(*out)).permute(0, 3, 1, 2).cpu().double()
+    assert got.shape == ref.shape
+    err = float((got - ref).abs().max())
+    assert err < tol * max(1.0, float(ref.abs().max())), err
