@@ -8,6 +8,7 @@ BatchNorm is folded to a per-channel scale/shift at weight-load time.
 """
 from __future__ import annotations
 
+import os
 from collections import namedtuple
 
 import numpy as np
@@ -24,7 +25,7 @@ arch_param_n = 128
 #   "tc3"  tcgen05, split-fp16 operands, 3 MMAs per product (fp32-class; the parity mode)
 #   "tc1"  tcgen05, fp16 operands, 1 MMA (fast mode; symbols no longer bit-exact)
 #   "simt" CUDA-core fp32 (v1 kernel, kept as the on-GPU cross-check)
-TRUNK_MODE = "tc3"
+TRUNK_MODE = os.environ.get("DSIN_TRUNK_MODE", "tc3")
 COMPUTE_DTYPE = "f16x2-split tensor-core (fp32 accumulate) + f32 CUDA-core"
 
 

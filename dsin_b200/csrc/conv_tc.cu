@@ -20,6 +20,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
 // warps 2-5 = epilogue (TMEM -> registers -> scale/shift/act/residual/post -> global).
 #include "tc_common.cuh"
+#include "conv_tc.cuh"
 
 using namespace tc;
 
@@ -36,7 +37,13 @@ struct GP {
   float* yf;
   int n, GH, GW, OH, OW, cout, os, py, px, in_step, act, post, ntaps, nchunks;
   int tiles_w, tiles_h, total_tiles;
-  short dy[MAX_TAPS], dx[MAX_TAPS], wi[MAX_TAPS];
+  short dy[MAX_TAPS], dx[MAX_TAPS], wi[MAX_TAPS], dz[MAX_TAPS];
+  // 3-D (VALID) mode: tile "image" index n = vol * dout + d; the A box comes from image
+  // vol * din + d + dz[tap].  dout == 0 means plain 2-D (image index passes through).
+  int dout, din;
+  // optional fp32 residual with its own geometry (cropped skip of the probability model)
+  const float* r1f;
+  int r1_d, r1_oh, r1_ow, r1_dz, r1_dy, r1_dx;
 };
 
 constexpr int up1024(int v) { return (v + 1023) / 1024 * 1024; }
@@ -145,10 +152,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
           uint8_t* st = tiles + stage * STAGE;
           mbar_expect_tx(&full[stage], kBytes);
           const int ax = x0 + p.dx[tap], ay = y0 + p.dy[tap], wrow = p.wi[tap] * NPAD;
-          tma_load_4d(st, &tm_xh, &full[stage], cc * KC, ax, ay, n);
+          const int n_in = p.dout ? (n / p.dout) * p.din + (n % p.dout) + p.dz[tap] : n;
+          tma_load_4d(st, &tm_xh, &full[stage], cc * KC, ax, ay, n_in);
           tma_load_2d(st + OFF_B, &tm_wh, &full[stage], cc * KC, wrow);
           if (TERMS == 3) {
-            tma_load_4d(st + OFF_ALO, &tm_xl, &full[stage], cc * KC, ax, ay, n);
+            tma_load_4d(st + OFF_ALO, &tm_xl, &full[stage], cc * KC, ax, ay, n_in);
             tma_load_2d(st + OFF_BLO, &tm_wl, &full[stage], cc * KC, wrow);
           }
           if (++stage == S) {
@@ -227,6 +235,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
             f[j] = t;
           }
           const size_t off = pix * p.cout + c0;
+          if (p.r1f) {
+            const size_t rpix = (((size_t)(n / p.dout) * p.r1_d + (n % p.dout) + p.r1_dz) * p.r1_oh + oy + p.r1_dy) *
+                                    p.r1_ow + ox + p.r1_dx;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.cout) f[j] = __fadd_rn(f[j], __ldg(p.r1f + rpix * p.cout + c0 + j));
+          }
           if (p.r1h) add_residual16(f, p.r1h, p.r1l, off);
           if (p.r2h) add_residual16(f, p.r2h, p.r2l, off);
           if (p.post != DSIN_POST_NONE) {
@@ -334,6 +349,47 @@ int npad_of(int cout) { return (cout + 15) / 16 * 16; }
 int kc_of(int cin) { return cin % 64 == 0 ? 64 : 32; }
 
 }  // namespace
+
+// Internal entry used by the probability model: VALID 3-D conv over a channels-last volume
+// (vols, D, H, W, 32 ch split fp16) with an explicit tap list; see conv_tc.cuh.
+int conv_tc_valid3d(dsin_handle_t h, const ConvTc3dArgs& a, cudaStream_t st) {
+  if (a.cin != 32 || a.ntaps < 1 || a.ntaps > MAX_TAPS)
+    return dsin_fail(h, DSIN_ERR_UNSUPPORTED, "%s: 3-D tensor-core conv needs cin == 32", __func__);
+  const int NPAD = npad_of(a.cout);
+  const int Do = a.D - a.kd + 1, Ho = a.H - a.kh + 1, Wo = a.W - a.kw + 1;
+  CUtensorMap xh, xl, wh, wl;
+  const uint64_t xd[4] = {32, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.vols * a.D};
+  const uint64_t xs[3] = {64, (uint64_t)a.W * 64, (uint64_t)a.H * a.W * 64};
+  const uint32_t xb[4] = {32, BW, BH, 1};
+  const uint64_t wd[2] = {32, (uint64_t)a.wtaps * NPAD};
+  const uint64_t wsb[1] = {64};
+  const uint32_t wb[2] = {32, (uint32_t)NPAD};
+  const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  bool ok = encode_tmap(&xh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.x_hi, xd, xs, xb, sw) &&
+            encode_tmap(&xl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.x_lo ? a.x_lo : a.x_hi, xd, xs, xb, sw) &&
+            encode_tmap(&wh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.w_hi, wd, wsb, wb, sw) &&
+            encode_tmap(&wl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.w_lo ? a.w_lo : a.w_hi, wd, wsb, wb, sw);
+  if (!ok) return dsin_fail(h, DSIN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", __func__);
+  GP p;
+  memset(&p, 0, sizeof(p));
+  p.scale = a.scale; p.shift = a.shift;
+  p.yh = (__half*)a.y_hi; p.yl = (__half*)a.y_lo; p.yf = a.y_f32;
+  p.n = a.vols * Do; p.cout = a.cout; p.act = a.act; p.post = DSIN_POST_NONE;
+  p.nchunks = 1; p.in_step = 1;
+  p.OH = Ho; p.OW = Wo; p.GH = Ho; p.GW = Wo; p.os = 1;
+  p.dout = Do; p.din = a.D;
+  p.ntaps = a.ntaps;
+  for (int t = 0; t < a.ntaps; ++t) {
+    p.dz[t] = a.tap_d[t]; p.dy[t] = a.tap_h[t]; p.dx[t] = a.tap_w[t]; p.wi[t] = a.tap_wi[t];
+  }
+  p.r1f = a.r1f; p.r1_d = a.r1_d; p.r1_oh = a.r1_oh; p.r1_ow = a.r1_ow;
+  p.r1_dz = a.r1_dz; p.r1_dy = a.r1_dy; p.r1_dx = a.r1_dx;
+  p.tiles_w = (p.GW + BW - 1) / BW; p.tiles_h = (p.GH + BH - 1) / BH;
+  p.total_tiles = p.n * p.tiles_w * p.tiles_h;
+  if (NPAD == 32) return launch_terms<32, 32>(h, a.terms, xh, xl, wh, wl, p, st);
+  if (NPAD == 16) return launch_terms<32, 16>(h, a.terms, xh, xl, wh, wl, p, st);
+  return dsin_fail(h, DSIN_ERR_UNSUPPORTED, "%s: unsupported cout", __func__);
+}
 
 extern "C" int dsin_conv_tc_npad(int cout) { return npad_of(cout); }
 

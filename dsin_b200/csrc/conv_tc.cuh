@@ -1,0 +1,19 @@
+// Internal (non-ABI) entry of the generic tensor-core conv for 3-D VALID convolutions.
+#pragma once
+#include "common.cuh"
+
+struct ConvTc3dArgs {
+  int vols, D, H, W;        // input volume (channels-last, 32 channels split fp16)
+  int kd, kh, kw;           // kernel extent (output = input - k + 1 per axis)
+  int cin, cout, terms, act;
+  int ntaps, wtaps;         // live taps / taps in the packed weight tensor
+  short tap_d[32], tap_h[32], tap_w[32], tap_wi[32];
+  const uint16_t *x_hi, *x_lo, *w_hi, *w_lo;
+  const float *scale, *shift;
+  uint16_t *y_hi, *y_lo;    // split output (cout % 16 == 0) or
+  float* y_f32;             // fp32 output (vols, Do, Ho, Wo, cout)
+  const float* r1f;         // optional fp32 residual volume (vols, r1_d, r1_oh, r1_ow, cout), read at +offsets
+  int r1_d, r1_oh, r1_ow, r1_dz, r1_dy, r1_dx;
+};
+
+int conv_tc_valid3d(dsin_handle_t h, const ConvTc3dArgs& a, cudaStream_t st);

@@ -6,6 +6,7 @@
 // dead (masked) taps skipped; layer 0 reads qbar with the centres[0] padding applied on the fly;
 // the last layer fuses ReLU + log-sum-exp cross entropy + log2(e) and the per-image fp64 sum.
 #include "common.cuh"
+#include "conv_tc.cuh"
 
 struct PcP {
   const float* in;     // layer input (N,Di,Hi,Wi,CIN) or qbar_nchw for the first layer
@@ -205,5 +206,103 @@ extern "C" int dsin_probclass_bits(dsin_handle_t h, const float* qbar, const int
     pc_conv3d_kernel<24, 6, false, true><<<(unsigned)((v3 + 127) / 128), 128, smem, st>>>(p);
     DSIN_LAUNCHED(h);
   }
+  return DSIN_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// tensor-core variant: the two 24->24 layers (88 % of the model's FLOPs) run on the generic tcgen05
+// conv (3-D VALID mode, channels padded 24 -> 32, split fp16); the 1->24 stem and the 24->6 layer with
+// its fused cross entropy stay on CUDA cores.
+// ---------------------------------------------------------------------------------------------
+__global__ void pc_pad_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
+                                    int64_t nvox, int cin, int cpad) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nvox * cpad) return;
+  int c = (int)(idx % cpad);
+  int64_t v = idx / cpad;
+  float f = c < cin ? x[v * cin + c] : 0.f;
+  __half h = __float2half_rn(f);
+  hi[idx] = h;
+  lo[idx] = __float2half_rn(f - __half2float(h));
+}
+
+static void pc_live_taps(ConvTc3dArgs& a) {
+  a.ntaps = 0;
+  for (int d = 0; d < 2; ++d)
+    for (int hh = 0; hh < 3; ++hh)
+      for (int ww = 0; ww < 3; ++ww) {
+        if (d == 1 && (hh > 1 || (hh == 1 && ww > 1))) continue;  // other_mask
+        a.tap_d[a.ntaps] = (short)d; a.tap_h[a.ntaps] = (short)hh; a.tap_w[a.ntaps] = (short)ww;
+        a.tap_wi[a.ntaps] = (short)(d * 9 + hh * 3 + ww);
+        a.ntaps++;
+      }
+  a.wtaps = 18;
+}
+
+extern "C" int64_t dsin_probclass_tc_workspace_bytes(int n, int c, int hh, int ww) {
+  int64_t v0 = (int64_t)n * (c + 3) * (hh + 6) * (ww + 6);
+  int64_t v1 = (int64_t)n * (c + 2) * (hh + 4) * (ww + 4);
+  int64_t v2 = (int64_t)n * (c + 1) * (hh + 2) * (ww + 2);
+  return v0 * 24 * 4 + v0 * 32 * 2 * 2 + v1 * 32 * 2 * 2 + v2 * 24 * 4 + 4096;
+}
+
+extern "C" int dsin_probclass_bits_tc(dsin_handle_t h, const float* qbar, const int64_t* symbols, int n, int c,
+                                      int hh, int ww, float pad_value, const float* w0, const float* b0,
+                                      const uint16_t* w1_hi, const uint16_t* w1_lo, const float* scale1,
+                                      const float* shift1, const uint16_t* w2_hi, const uint16_t* w2_lo,
+                                      const float* scale2, const float* shift2, const float* w3, const float* b3,
+                                      int terms, float* bits_nchw, double* bits_sum, void* workspace, void* stream) {
+  DSIN_REQUIRE(h, qbar && symbols && bits_sum && workspace, "null pointer");
+  DSIN_REQUIRE(h, w0 && b0 && w1_hi && w1_lo && scale1 && shift1 && w2_hi && w2_lo && scale2 && shift2 && w3 && b3,
+               "null weights");
+  DSIN_REQUIRE(h, hh + 2 >= 8 && ww + 2 >= 16, "volume smaller than one tile");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int k = 24;
+  int64_t v0 = (int64_t)n * (c + 3) * (hh + 6) * (ww + 6);
+  int64_t v1 = (int64_t)n * (c + 2) * (hh + 4) * (ww + 4);
+  int64_t v2 = (int64_t)n * (c + 1) * (hh + 2) * (ww + 2);
+  uint8_t* base = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  float* a0 = (float*)base;                       base += (v0 * 24 * 4 + 255) / 256 * 256;
+  __half* x1h = (__half*)base;                    base += (v0 * 32 * 2 + 255) / 256 * 256;
+  __half* x1l = (__half*)base;                    base += (v0 * 32 * 2 + 255) / 256 * 256;
+  __half* y1h = (__half*)base;                    base += (v1 * 32 * 2 + 255) / 256 * 256;
+  __half* y1l = (__half*)base;                    base += (v1 * 32 * 2 + 255) / 256 * 256;
+  float* a2 = (float*)base;
+  if (cudaMemsetAsync(bits_sum, 0, sizeof(double) * n, st) != cudaSuccess)
+    return dsin_fail(h, DSIN_ERR_CUDA, "%s: memset failed", __func__);
+  PcP p;
+  memset(&p, 0, sizeof(p));
+  p.n = n; p.c = c; p.hh = hh; p.ww = ww; p.pad_value = pad_value;
+  // layer 0 (CUDA cores): padded (c+4, hh+8, ww+8, 1) -> (c+3, hh+6, ww+6, 24), ReLU
+  p.in = qbar; p.w = w0; p.b = b0; p.out = a0; p.Di = c + 4; p.Hi = hh + 8; p.Wi = ww + 8;
+  p.live_mask = pc_live_mask(true); p.relu = 1;
+  pc_conv3d_kernel<1, 24, true, false><<<(unsigned)((v0 + 127) / 128), 128, (18 * 24 + 24) * sizeof(float), st>>>(p);
+  DSIN_LAUNCHED(h);
+  pc_pad_split_kernel<<<(unsigned)((v0 * 32 + 255) / 256), 256, 0, st>>>(a0, x1h, x1l, v0, k, 32);
+  DSIN_LAUNCHED(h);
+  // res1/conv1 (tcgen05): ReLU, 32-channel (24 + 8 zero) split output
+  ConvTc3dArgs a;
+  memset(&a, 0, sizeof(a));
+  pc_live_taps(a);
+  a.vols = n; a.D = c + 3; a.H = hh + 6; a.W = ww + 6; a.kd = 2; a.kh = 3; a.kw = 3;
+  a.cin = 32; a.cout = 32; a.terms = terms; a.act = DSIN_ACT_RELU;
+  a.x_hi = (const uint16_t*)x1h; a.x_lo = (const uint16_t*)x1l; a.w_hi = w1_hi; a.w_lo = w1_lo;
+  a.scale = scale1; a.shift = shift1; a.y_hi = (uint16_t*)y1h; a.y_lo = (uint16_t*)y1l;
+  int rc = conv_tc_valid3d(h, a, st);
+  if (rc != DSIN_OK) return rc;
+  // res1/conv2 (tcgen05): no activation, + skip a0[2:, 2:-2, 2:-2], fp32 24-channel output
+  a.D = c + 2; a.H = hh + 4; a.W = ww + 4; a.cout = 24; a.act = DSIN_ACT_NONE;
+  a.x_hi = (const uint16_t*)y1h; a.x_lo = (const uint16_t*)y1l; a.w_hi = w2_hi; a.w_lo = w2_lo;
+  a.scale = scale2; a.shift = shift2; a.y_hi = nullptr; a.y_lo = nullptr; a.y_f32 = a2;
+  a.r1f = a0; a.r1_d = c + 3; a.r1_oh = hh + 6; a.r1_ow = ww + 6; a.r1_dz = 2; a.r1_dy = 2; a.r1_dx = 2;
+  rc = conv_tc_valid3d(h, a, st);
+  if (rc != DSIN_OK) return rc;
+  // conv2: 24 -> 6, ReLU, fused cross entropy (CUDA cores)
+  p.in = a2; p.w = w3; p.b = b3; p.out = nullptr; p.skip = nullptr; p.Di = c + 1; p.Hi = hh + 2; p.Wi = ww + 2;
+  p.live_mask = pc_live_mask(false); p.relu = 1; p.sym = symbols; p.bits = bits_nchw; p.bits_sum = bits_sum;
+  int64_t v3 = (int64_t)n * c * hh * ww;
+  pc_conv3d_kernel<24, 6, false, true><<<(unsigned)((v3 + 127) / 128), 128, (18 * 24 * 6 + 6) * sizeof(float), st>>>(p);
+  DSIN_LAUNCHED(h);
   return DSIN_OK;
 }

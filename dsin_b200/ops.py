@@ -270,6 +270,52 @@ def probclass_bits(qbar_nchw, symbols, weights, pad_value, k=24, L=6, want_bits=
     return bits, sums
 
 
+class ProbclassTC(object):
+    """Packed tensor-core weights of the two 24->24 probclass layers (channels zero-padded to 32)."""
+
+    def __init__(self, weights):
+        h = handle()
+        (w0, b0), (w1, b1), (w2, b2), (w3, b3) = weights
+        dev = w0.device
+        self.w0, self.b0, self.w3, self.b3 = w0, b0, w3, b3
+
+        def pack(w, b, cout_pad):
+            wp = torch.zeros((18, 32, cout_pad), dtype=torch.float32, device=dev)
+            wp[:, :24, :24] = w.reshape(18, 24, 24)
+            bp = torch.zeros((cout_pad,), dtype=torch.float32, device=dev)
+            bp[:24] = b
+            npad = int(h.lib.dsin_conv_tc_npad(cout_pad))
+            hi = torch.empty((18, npad, 32), dtype=torch.float16, device=dev)
+            lo = torch.empty((18, npad, 32), dtype=torch.float16, device=dev)
+            ws = torch.empty((cout_pad,), dtype=torch.float32, device=dev)
+            h.check(h.lib.dsin_pack_conv_w_tc(h.ptr, _p(wp), 18, 32, cout_pad, _p(hi), _p(lo), _p(ws), _stream()))
+            return hi, lo, (1.0 / ws).contiguous(), bp
+
+        self.l1 = pack(w1, b1, 32)
+        self.l2 = pack(w2, b2, 24)
+
+
+def probclass_bits_tc(qbar_nchw, symbols, pctc, pad_value, terms=3, want_bits=True):
+    h = handle()
+    n, c, hh, ww = qbar_nchw.shape
+    dev = qbar_nchw.device
+    ws = int(h.lib.dsin_probclass_tc_workspace_bytes(n, c, hh, ww))
+    work = torch.empty(ws, dtype=torch.uint8, device=dev)
+    bits = torch.empty((n, c, hh, ww), dtype=torch.float32, device=dev) if want_bits else None
+    sums = torch.empty((n,), dtype=torch.float64, device=dev)
+    e0 = PROF.begin()
+    h.check(h.lib.dsin_probclass_bits_tc(
+        h.ptr, _p(_chk(qbar_nchw)), _p(_chk(symbols, torch.int64)), n, c, hh, ww, C.c_float(float(pad_value)),
+        _p(pctc.w0), _p(pctc.b0), _p(pctc.l1[0]), _p(pctc.l1[1]), _p(pctc.l1[2]), _p(pctc.l1[3]),
+        _p(pctc.l2[0]), _p(pctc.l2[1]), _p(pctc.l2[2]), _p(pctc.l2[3]), _p(pctc.w3), _p(pctc.b3), terms,
+        _p(bits), _p(sums), _p(work), _stream()))
+    if e0 is not None:
+        vox = lambda a, b_, c_: float(n * (c + a) * (hh + b_) * (ww + c_))  # noqa: E731
+        PROF.end(e0, "probclass_tc%d" % terms, 2.0 * 18 * (vox(3, 6, 6) * 24 + vox(2, 4, 4) * 576 + vox(1, 2, 2) * 576
+                                                           + vox(0, 0, 0) * 144))
+    return bits, sums
+
+
 def sif_prepare(xdec_nhwc, ydec_nhwc, ph, pw):
     h = handle()
     n, hh, ww, _ = xdec_nhwc.shape
@@ -309,3 +355,36 @@ def sif_gather(y_nhwc, row, col, ph, pw):
     h.check(h.lib.dsin_sif_gather(h.ptr, _p(_chk(y_nhwc)), _p(_chk(row, torch.int32)), _p(_chk(col, torch.int32)), n,
                                   hh, ww, ph, pw, _p(out), _stream()))
     return out
+
+
+MSSSIM_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)  # ms_ssim_np_imgcomp.py:91-92
+
+
+def msssim_levels(img1, img2, groups, batch, height, width, depth):
+    """fp32 CUDA tensors viewed as (groups, batch, height, width, depth) -> (groups, 5, 2) float64 CUDA
+    tensor of per-level mean SSIM / mean CS."""
+    h = handle()
+    dev = img1.device
+    assert img1.numel() == img2.numel() == groups * batch * height * width * depth
+    ws = int(h.lib.dsin_msssim_workspace_bytes(groups, batch, height, width, depth))
+    work = torch.empty(ws, dtype=torch.uint8, device=dev)
+    out = torch.empty((groups, 5, 2), dtype=torch.float64, device=dev)
+    h.check(h.lib.dsin_msssim(h.ptr, _p(_chk(img1)), _p(_chk(img2)), groups, batch, height, width, depth, _p(out),
+                              _p(work), _stream()))
+    return out
+
+
+def msssim(img1_nhwc, img2_nhwc, form="standard"):
+    """Per-image MS-SSIM of (N,H,W,C) fp32 CUDA tensors -> float64 numpy (N,).
+    form="standard": each image as (1,H,W,C); form="reference_call": the reference's literal
+    utils.msssim_x_vs_rec view (H,W,C,1) -> batch=H, height=W, width=C, depth=1."""
+    n, hh, ww, c = img1_nhwc.shape
+    if form == "standard":
+        lv = msssim_levels(img1_nhwc, img2_nhwc, n, 1, hh, ww, c)
+    elif form == "reference_call":
+        lv = msssim_levels(img1_nhwc, img2_nhwc, n, hh, ww, c, 1)
+    else:
+        raise ValueError(form)
+    lv = lv.cpu().numpy()
+    w = np.array(MSSSIM_WEIGHTS)
+    return np.prod(lv[:, :4, 1] ** w[:4], axis=1) * (lv[:, 4, 0] ** w[4])

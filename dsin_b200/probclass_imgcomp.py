@@ -6,10 +6,16 @@ Mirrors /root/reference/src/probclass_imgcomp.py: ``get_network_cls``, ``_Networ
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
 from . import ops, synth
+
+
+# "tc3"/"tc1": the two 24->24 layers on tcgen05 (split fp16 / fp16); "simt": all CUDA cores
+MODE = os.environ.get("DSIN_PROBCLASS_MODE", "tc3")
 
 
 def get_network_cls(pc_config):
@@ -37,6 +43,7 @@ class _ResShallow(object):
             raise ValueError("only kernel_size 3 is built")
         self.first_mask, self.other_mask = create_masks(pc_config.kernel_size)
         self.weights = None
+        self._tc = None
         self.device = "cuda"
 
     @classmethod
@@ -62,6 +69,7 @@ class _ResShallow(object):
             out.append((torch.from_numpy(np.ascontiguousarray(w)).to(self.device),
                         torch.from_numpy(np.ascontiguousarray(b)).to(self.device)))
         self.weights = out
+        self._tc = None
 
     def bitcost(self, q, target_symbols, is_training=False, pad_value=0):
         """q: qbar NCHW fp32, target_symbols NCHW int64 -> bits per symbol NCHW.  The fp64
@@ -70,7 +78,14 @@ class _ResShallow(object):
             raise NotImplementedError("dsin_b200 implements the inference path only")
         if q.dim() != 4:
             raise ValueError("expected NCHW, got {}".format(tuple(q.shape)))
-        bits, sums = ops.probclass_bits(q.contiguous(), target_symbols.contiguous(), self.weights,
-                                        float(pad_value), k=self.config.arch_param__k, L=self.L)
+        n, c, hh, ww = q.shape
+        if MODE in ("tc3", "tc1") and hh + 2 >= 8 and ww + 2 >= 16 and self.config.arch_param__k == 24:
+            if self._tc is None:
+                self._tc = ops.ProbclassTC(self.weights)
+            bits, sums = ops.probclass_bits_tc(q.contiguous(), target_symbols.contiguous(), self._tc,
+                                               float(pad_value), terms=3 if MODE == "tc3" else 1)
+        else:
+            bits, sums = ops.probclass_bits(q.contiguous(), target_symbols.contiguous(), self.weights,
+                                            float(pad_value), k=self.config.arch_param__k, L=self.L)
         bits._dsin_sum = sums
         return bits

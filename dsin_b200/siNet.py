@@ -7,13 +7,15 @@ y_syn_nhwc)`` additionally fuses the normalise+concat in front (src/AE.py:67-68)
 de-normalisation behind (src/AE.py:69)."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import ops, synth
 
 
 # "tc3": tcgen05 split-fp16 (fp32-class); "tc1": tcgen05 fp16; "simt": CUDA-core fp32
-MODE = "tc3"
+MODE = os.environ.get("DSIN_SINET_MODE", "tc3")
 
 
 class SiNet(object):

@@ -127,6 +127,17 @@ int dsin_probclass_bits(dsin_handle_t h, const float* qbar_nchw, const int64_t* 
                         const float* b2, const float* w3, const float* b3, float* bits_nchw,
                         double* bits_sum, void* workspace, void* stream);
 
+/* Tensor-core variant: the two 24->24 layers run on tcgen05 (weights packed by dsin_pack_conv_w_tc
+ * from [18][32][32] / [18][32][24] zero-padded fp32 tensors, scale = 1/wscale, shift = bias); the 1->24
+ * stem (w0,b0) and the 24->6 layer with the fused cross entropy (w3,b3) stay on CUDA cores. */
+int64_t dsin_probclass_tc_workspace_bytes(int n, int c, int hh, int ww);
+int dsin_probclass_bits_tc(dsin_handle_t h, const float* qbar_nchw, const int64_t* symbols, int n, int c,
+                           int hh, int ww, float pad_value, const float* w0, const float* b0,
+                           const uint16_t* w1_hi, const uint16_t* w1_lo, const float* scale1,
+                           const float* shift1, const uint16_t* w2_hi, const uint16_t* w2_lo,
+                           const float* scale2, const float* shift2, const float* w3, const float* b3,
+                           int terms, float* bits_nchw, double* bits_sum, void* workspace, void* stream);
+
 /* ---- K5-K7: SI-Finder ---------------------------------------------------------------------
  * Replaces SI_full_img (src/siFull_img.py:5-68), siFinder (src/siFinder.py:7-53),
  * reduce_mean_and_std_normalize_images (:56-73), rgb_transform (:138-154),
@@ -155,6 +166,16 @@ int dsin_sif_match(dsin_handle_t h, const float* q, const float* r, const float*
                    void* stream);
 int dsin_sif_gather(dsin_handle_t h, const float* y_nhwc, const int32_t* row, const int32_t* col,
                     int n, int hh, int ww, int ph, int pw, float* ysyn_nhwc, void* stream);
+
+/* ---- K9: MS-SSIM, the metric of record ---------------------------------------------------------
+ * Replaces ms_ssim_np_imgcomp.MultiScaleSSIM/_SSIMForMultiScale/_FSpecialGauss
+ * (src/ms_ssim_np_imgcomp.py:51-200) as called by utils.msssim_x_vs_rec (src/utils.py:94-99), in
+ * float64 on the device.  img1/img2: fp32 (groups, batch, height, width, depth); each group is reduced
+ * separately (one group = one image).  out: (groups, 5, 2) doubles = per-level mean SSIM and mean CS;
+ * MS-SSIM = prod_{l<4} cs_l^w_l * ssim_4^w_4 with the weights of ms_ssim_np_imgcomp.py:91-92. */
+int64_t dsin_msssim_workspace_bytes(int groups, int batch, int height, int width, int depth);
+int dsin_msssim(dsin_handle_t h, const float* img1, const float* img2, int groups, int batch, int height,
+                int width, int depth, double* out_g52, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -361,3 +361,49 @@ def test_generic_conv_tc_matches_float64(case, terms, tol):
     assert got.shape == ref.shape
     err = float((got - ref).abs().max())
     assert err < tol * max(1.0, float(ref.abs().max())), err
+
+
+# ----------------------------------------------------------------------------- K9 MS-SSIM
+def test_msssim_kernel_matches_reference_golden(golden_dir):
+    """Device MS-SSIM (fp64) vs the values the reference's own numpy/scipy module produced
+    (tests/golden/msssim_golden.npz), both call forms."""
+    import os
+    from dsin_b200 import utils
+    g = np.load(os.path.join(golden_dir, "msssim_golden.npz"))
+    for k in (0, 1):
+        img, rec = g["img_%d" % k], g["rec_%d" % k].astype(np.float32)
+        assert float(utils.msssim_standard(img, rec)) == pytest.approx(float(g["std_%d" % k]), abs=2e-7)
+        assert float(utils.msssim_x_vs_rec(img, rec)) == pytest.approx(float(g["utils_%d" % k]), abs=2e-7)
+
+
+def test_msssim_kernel_batch_matches_oracle_full_size():
+    from dsin_b200 import ops
+    x, y = synth.make_batch(2, 320, 1224, seed=77)
+    rec = np.clip(x + np.random.default_rng(0).normal(0, 6, x.shape), 0, 255).astype(np.float32)
+    got = ops.msssim(_nhwc(_dev(x)), _nhwc(_dev(rec)), form="standard")
+    got2 = ops.msssim(_nhwc(_dev(x)), _nhwc(_dev(rec)), form="reference_call")
+    for n in range(2):
+        xi, ri = np.transpose(x[n], (1, 2, 0)), np.transpose(rec[n], (1, 2, 0))
+        assert got[n] == pytest.approx(float(M.multi_scale_ssim(xi[None], ri[None])), abs=1e-9)
+        assert got2[n] == pytest.approx(float(M.multi_scale_ssim(xi[..., None], ri[..., None])), abs=1e-9)
+
+
+@pytest.mark.parametrize("mode", ["simt", "tc3"])
+def test_probclass_modes_match_oracle(mode):
+    from dsin_b200 import probclass_imgcomp as pcm
+    W = calibrated_weights(0)
+    old = pcm.MODE
+    pcm.MODE = mode
+    try:
+        ae = make_ae(80, 144, W)
+        rng = np.random.default_rng(6)
+        c = W[O.ENC + "centers"]
+        sym = torch.tensor(rng.integers(0, 6, (2, 32, 40, 153)))
+        q = torch.tensor(c)[sym]
+        ref = O.probclass_bitcost(q, sym, W)
+        bits = ae.pc_imgcomp.bitcost(q.cuda(), sym.cuda(), is_training=False, pad_value=float(c[0]))
+        assert float((bits.cpu() - ref).abs().max()) < 1e-4
+        sums = bits._dsin_sum.cpu()
+        assert torch.allclose(sums, ref.double().reshape(2, -1).sum(1), rtol=2e-7)
+    finally:
+        pcm.MODE = old
