@@ -42,12 +42,18 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * TN * 8 + 1024 /*align*/ + 
 struct SifP {
   const float4* ystat;   // (n,hp,wp): sum_y, mean_y, den_y, sum_y2
   const float4* pinfo;   // (n,P): sum of fp16 centred patch, rsqrt(den_x), cy', cx'
-  float2* cand;          // (n,P,units,TOPK): coarse score, position index (as int bits)
+  float2* cand;          // (n,P,rgroups,2,TOPK): coarse score, position index (as int bits)
   int n, hp, wp, P, ptiles, rgroups, jtiles, total_units, use_mask;
   float kh, kw;          // -4/sigma_h^2, -4/sigma_w^2 (exp2 form of exp(-4 ln2 t))
 };
 
-__global__ void __launch_bounds__(192, 1)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(320, 1)
 sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_s, SifP p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -68,7 +74,7 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     fence_barrier_init();
     prefetch_tmap(&tm_q);
@@ -145,9 +151,12 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps 2..5
+    // ------------------------------------------------------------ epilogue warps 2..9
+    // Two warps per TMEM lane quarter; each scores half of the tile's 256 positions for its 32 patches
+    // and keeps its own running top-4 (flushed per work unit, so a patch has 8 candidates per unit).
     const int q = warp & 3;
-    const int et = (warp - 2) * 32 + lane;  // 0..127 among epilogue threads
+    const int half = (warp - 2) >> 2;
+    const int et = (warp - 2) * 32 + lane;  // 0..255 among epilogue threads
     int it = 0;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const int img = u / units_per_img, r = u % units_per_img;
@@ -156,19 +165,14 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       const bool pvalid = pch < p.P;
       float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
       if (pvalid) pi = p.pinfo[(size_t)img * p.P + pch];
-      float bs[TOPK];
-      int bi[TOPK];
-#pragma unroll
-      for (int k = 0; k < TOPK; ++k) {
-        bs[k] = -INFINITY;
-        bi[k] = -1;
-      }
+      float bs0 = -INFINITY, bs1 = -INFINITY, bs2 = -INFINITY, bs3 = -INFINITY;
+      int bi0 = -1, bi1 = -1, bi2 = -1, bi3 = -1;
       const int i1 = min(p.hp, (rg + 1) * ROWS_PER_UNIT);
       for (int i = rg * ROWS_PER_UNIT; i < i1; ++i) {
         float rowf = pi.y;  // rsqrt(den_x) * row factor of the prior
         if (p.use_mask) {
           float dh = (float)i - pi.z;
-          rowf *= exp2f(p.kh * dh * dh);
+          rowf *= ex2_approx(p.kh * dh * dh);
         }
         for (int jt = 0; jt < p.jtiles; ++jt, ++it) {
           const int acc = it & 1;
@@ -176,48 +180,46 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           const int nvalid = min(TN, p.wp - j0);
           // stage per-position statistics for this tile (double buffered with the accumulator)
           float2* sp = s_pos + acc * TN;
-#pragma unroll
-          for (int c = et; c < TN; c += 128) {
+          {
             float2 v = make_float2(0.f, 0.f);
-            if (c < nvalid) {
-              float4 ys = __ldg(p.ystat + ((size_t)img * p.hp + i) * p.wp + j0 + c);
+            if (et < nvalid) {
+              float4 ys = __ldg(p.ystat + ((size_t)img * p.hp + i) * p.wp + j0 + et);
               v.x = ys.y;
               v.y = ys.z > 0.f ? rsqrtf(ys.z) : 0.f;
             }
-            sp[c] = v;
+            sp[et] = v;
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u);
           fence_after_sync();
 #pragma unroll 1
-          for (int chunk = 0; chunk < TN / 32; ++chunk) {
-            if (chunk * 32 >= nvalid) break;  // warp-uniform
+          for (int chunk = 0; chunk < TN / 64; ++chunk) {
+            const int cb = half * (TN / 2) + chunk * 32;
+            if (cb >= nvalid) break;  // warp-uniform
             uint32_t v[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + chunk * 32), v);
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + cb), v);
             tmem_ld_wait();
-            if (pvalid) {
 #pragma unroll
-              for (int jj = 0; jj < 32; ++jj) {
-                const int c = chunk * 32 + jj;
-                const float2 ps = sp[c];
-                float s = (__uint_as_float(v[jj]) - ps.x * pi.x) * ps.y * rowf;
-                if (p.use_mask) {
-                  float dw = (float)(j0 + c) - pi.w;
-                  s *= exp2f(p.kw * dw * dw);
-                }
-                if (c < nvalid && s > bs[TOPK - 1]) {
+            for (int jj = 0; jj < 32; ++jj) {
+              const int c = cb + jj;
+              const float2 ps = sp[c];
+              float s = (__uint_as_float(v[jj]) - ps.x * pi.x) * ps.y * rowf;
+              if (p.use_mask) {
+                float dw = (float)(j0 + c) - pi.w;
+                s *= ex2_approx(p.kw * dw * dw);
+              }
+              const bool pass = pvalid && c < nvalid && s > bs3;
+              if (__any_sync(0xffffffffu, pass)) {  // rare after warm-up; the branch is warp-uniform
+                if (pass) {
                   const int idx = i * p.wp + j0 + c;
-                  if (s > bs[0]) {
-                    bs[3] = bs[2]; bi[3] = bi[2]; bs[2] = bs[1]; bi[2] = bi[1]; bs[1] = bs[0]; bi[1] = bi[0];
-                    bs[0] = s; bi[0] = idx;
-                  } else if (s > bs[1]) {
-                    bs[3] = bs[2]; bi[3] = bi[2]; bs[2] = bs[1]; bi[2] = bi[1];
-                    bs[1] = s; bi[1] = idx;
-                  } else if (s > bs[2]) {
-                    bs[3] = bs[2]; bi[3] = bi[2];
-                    bs[2] = s; bi[2] = idx;
+                  if (s > bs0) {
+                    bs3 = bs2; bi3 = bi2; bs2 = bs1; bi2 = bi1; bs1 = bs0; bi1 = bi0; bs0 = s; bi0 = idx;
+                  } else if (s > bs1) {
+                    bs3 = bs2; bi3 = bi2; bs2 = bs1; bi2 = bi1; bs1 = s; bi1 = idx;
+                  } else if (s > bs2) {
+                    bs3 = bs2; bi3 = bi2; bs2 = s; bi2 = idx;
                   } else {
-                    bs[3] = s; bi[3] = idx;
+                    bs3 = s; bi3 = idx;
                   }
                 }
               }
@@ -229,9 +231,11 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         }
       }
       if (pvalid) {
-        float2* dst = p.cand + (((size_t)img * p.P + pch) * p.rgroups + rg) * TOPK;
-#pragma unroll
-        for (int k = 0; k < TOPK; ++k) dst[k] = make_float2(bs[k], __int_as_float(bi[k]));
+        float2* dst = p.cand + ((((size_t)img * p.P + pch) * p.rgroups + rg) * 2 + half) * TOPK;
+        dst[0] = make_float2(bs0, __int_as_float(bi0));
+        dst[1] = make_float2(bs1, __int_as_float(bi1));
+        dst[2] = make_float2(bs2, __int_as_float(bi2));
+        dst[3] = make_float2(bs3, __int_as_float(bi3));
       }
     }
   }
@@ -354,7 +358,7 @@ Layout make_layout(int n, int hh, int ww, int ph, int pw) {
   L.ptiles = (P + 127) / 128;
   L.rgroups = (hp + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
   L.jtiles = (wp + TN - 1) / TN;
-  L.ncand = L.rgroups * TOPK;
+  L.ncand = L.rgroups * 2 * TOPK;  // two epilogue warps (column halves) per patch
   auto up = [](int64_t v) { return (v + 1023) / 1024 * 1024; };
   L.q2 = 0;
   L.strip = up((int64_t)n * P * KQ * 2);
@@ -419,7 +423,7 @@ int sif_tc_match(dsin_handle_t h, const float* q, const float* r, const float* p
     configured = true;
   }
   const int grid = p.total_units < h->sm_count ? p.total_units : h->sm_count;
-  sif_tc_kernel<<<grid, 192, SMEM_BYTES, st>>>(tm_q, tm_s, p);
+  sif_tc_kernel<<<grid, 320, SMEM_BYTES, st>>>(tm_q, tm_s, p);
   DSIN_LAUNCHED(h);
   sif_rescore_kernel<<<(unsigned)((np * 32 + 255) / 256), 256, 0, st>>>(cand, L.ncand, q, r, pstat, ystat, n, hh, ww,
                                                                    ph, pw, use_mask, keys);
