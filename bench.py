@@ -188,11 +188,12 @@ def run_ours(args, rank, world, local_rank):
     host_sets = []
     for s in range(NSETS):
         x, y = synth.make_batch(B, H, W, seed=1000 * (rank + 1) + 17 * s)
-        px, py = ae.pinned_like(x.shape), ae.pinned_like(y.shape)
-        px.numpy()[...] = x
-        py.numpy()[...] = y
+        # host inputs are uint8 NCHW, as the reference's DataProvider delivers them (src/DataProvider.py:197-199)
+        px, py = ae.pinned_like(x.shape, np.uint8), ae.pinned_like(y.shape, np.uint8)
+        px.numpy()[...] = x.astype(np.uint8)
+        py.numpy()[...] = y.astype(np.uint8)
         host_sets.append((px, py))
-    dev_sets = [(px.to(dev), py.to(dev)) for px, py in host_sets]
+    dev_sets = [(px.to(dev).float(), py.to(dev).float()) for px, py in host_sets]
 
     def step_device(i):
         xd, yd = dev_sets[i % NSETS]
@@ -241,7 +242,7 @@ def run_ours(args, rank, world, local_rank):
         y_dec, y_syn, x_dec, x_with_si, bpp = ae.siNet_get_reconstructed(*host_sets[i % NSETS])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    h2d = 2 * B * 3 * H * W * 4
+    h2d = 2 * B * 3 * H * W * 1  # uint8 images
     d2h = 4 * B * 3 * H * W * 4 + 8 * B
 
     # ---------------- reductions over ranks ----------------

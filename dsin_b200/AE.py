@@ -63,6 +63,7 @@ class AE(object):
         self.set_weights(weights if weights is not None else synth.make_weights(seed))
         self._pinned = {}
         self._ring = 0
+        self._copy_stream = None
         self.last = {}
 
     # ------------------------------------------------------------------ weights
@@ -140,12 +141,16 @@ class AE(object):
         return [b.numpy() for b in outs]
 
     # ------------------------------------------------------------------ inference
-    def reconstruct_device(self, x, y):
-        """Device-resident variant: x, y (B,3,H,W) fp32 CUDA tensors -> dict of CUDA tensors."""
+    def reconstruct_device(self, x, y, on_decoded=None):
+        """Device-resident variant: x, y (B,3,H,W) fp32 CUDA tensors -> dict of CUDA tensors.
+        on_decoded(dec) is called as soon as the decoder output (2B,3,H,W) = [y_dec; x_dec] is enqueued,
+        so a caller can start copying it out while the SI-Finder and SI-Net run."""
         B = x.shape[0]
         both = torch.cat([y, x], dim=0)
         z = self._encode(both, self.ae_imgcomp, is_training=False)
         dec = self._decode(z.qbar, self.ae_imgcomp, is_training=False)
+        if on_decoded is not None:
+            on_decoded(dec)
         dec_nhwc = dec._dsin_nhwc
         y_dec, x_dec = dec[:B], dec[B:]
         y_dec._dsin_nhwc, x_dec._dsin_nhwc = dec_nhwc[:B], dec_nhwc[B:]
@@ -173,16 +178,56 @@ class AE(object):
                     "best": getattr(y_syn, "_dsin_best", None)})
         return out
 
+    def _pinned_out(self, name, shape, dtype):
+        key = ("out", name, self._ring, tuple(shape))
+        buf = self._pinned.get(key)
+        if buf is None:
+            buf = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+            self._pinned[key] = buf
+        return buf
+
     def siNet_get_reconstructed(self, x, y):
-        """x, y: (B,3,H,W) arrays (uint8 or float32, uint8-valued).  Returns numpy
-        (y_dec, y_syn, x_dec, x_with_si, bpp) like src/AE.py:148.  The returned arrays are
-        views of pinned staging buffers that are recycled two calls later."""
+        """x, y: (B,3,H,W) arrays, uint8 (what the reference's DataProvider yields,
+        src/DataProvider.py:197-199) or float32 holding uint8 values.  Returns numpy
+        (y_dec, y_syn, x_dec, x_with_si, bpp) like src/AE.py:148.  The returned arrays are views of
+        pinned staging buffers that are recycled two calls later.  The copy-out of y_dec/x_dec runs on
+        a side stream while the SI-Finder and SI-Net are still computing."""
         xd, yd = self._to_device(x, "x"), self._to_device(y, "y")
-        out = self.reconstruct_device(xd, yd)
-        y_dec, y_syn, x_dec, x_with_si = self._to_host([out["y_dec"], out["y_syn"], out["x_dec"], out["x_with_si"]])
-        bpp = bits.bitcost_to_bpp(out["bits"], xd)
+        self._ring ^= 1
+        main = torch.cuda.current_stream()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        B = xd.shape[0]
+        early = {}
+
+        overlap = os.environ.get("DSIN_E2E_OVERLAP", "1") != "0"
+
+        def on_decoded(dec):
+            buf = self._pinned_out("dec", dec.shape, dec.dtype)
+            if not overlap:
+                early["dev"] = dec
+                early["dec"] = buf
+                return
+            self._copy_stream.wait_stream(main)
+            with torch.cuda.stream(self._copy_stream):
+                buf.copy_(dec, non_blocking=True)
+            dec.record_stream(self._copy_stream)
+            early["dec"] = buf
+
+        out = self.reconstruct_device(xd, yd, on_decoded=on_decoded)
+        if "dev" in early:
+            early["dec"].copy_(early["dev"], non_blocking=True)
+        tail = []
+        for name in ("y_syn", "x_with_si"):
+            buf = self._pinned_out(name, out[name].shape, out[name].dtype)
+            buf.copy_(out[name], non_blocking=True)
+            tail.append(buf)
+        bpp = bits.bitcost_to_bpp(out["bits"], xd)  # reads the fp64 bit sums (synchronises `main`)
+        main.synchronize()
+        self._copy_stream.synchronize()
+        dec_host = early["dec"].numpy()
         self.last = out
-        return y_dec, y_syn, x_dec, x_with_si, bpp
+        return dec_host[:B], tail[0].numpy(), dec_host[B:], tail[1].numpy(), bpp
 
     def create_y_dec(self, y):
         yd = self._to_device(y, "y")

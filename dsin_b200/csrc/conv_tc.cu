@@ -50,9 +50,13 @@ constexpr int up1024(int v) { return (v + 1023) / 1024 * 1024; }
 
 template <int KC, int NPAD, int TERMS>
 struct Cfg {
+  // k-blocks (tap, channel chunk) per pipeline stage: the 32-channel layers have so little MMA work per
+  // k-block (N <= 128, K = 32) that the fixed per-stage cost dominates; they take 3 k-blocks per stage.
+  static constexpr int kTps = KC == 32 ? 3 : 1;
   static constexpr int kA = up1024(128 * KC * 2);
   static constexpr int kB = up1024(NPAD * KC * 2);
-  static constexpr int kStage = (TERMS == 3 ? 2 : 1) * (kA + kB);
+  static constexpr int kSub = (TERMS == 3 ? 2 : 1) * (kA + kB);
+  static constexpr int kStage = kTps * kSub;
   static constexpr int kStagesRaw = (196 * 1024) / kStage;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kSmem = kStages * kStage + 1024 + 2048;
@@ -94,6 +98,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
   using C = Cfg<KC, NPAD, TERMS>;
   constexpr int S = C::kStages;
   constexpr int STAGE = C::kStage;
+  constexpr int TPS = C::kTps;
   constexpr int OFF_B = C::kA, OFF_ALO = C::kA + C::kB, OFF_BLO = 2 * C::kA + C::kB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -146,18 +151,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
         const int tw = tile % p.tiles_w, t2 = tile / p.tiles_w;
         const int th = t2 % p.tiles_h, n = t2 / p.tiles_h;
         const int x0 = tw * BW * p.in_step, y0 = th * BH * p.in_step;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / p.nchunks, cc = kb - tap * p.nchunks;
+        for (int kb0 = 0; kb0 < num_kb; kb0 += TPS) {
+          const int nsub = min(TPS, num_kb - kb0);
           mbar_wait(&empty[stage], phase ^ 1u);
-          uint8_t* st = tiles + stage * STAGE;
-          mbar_expect_tx(&full[stage], kBytes);
-          const int ax = x0 + p.dx[tap], ay = y0 + p.dy[tap], wrow = p.wi[tap] * NPAD;
-          const int n_in = p.dout ? (n / p.dout) * p.din + (n % p.dout) + p.dz[tap] : n;
-          tma_load_4d(st, &tm_xh, &full[stage], cc * KC, ax, ay, n_in);
-          tma_load_2d(st + OFF_B, &tm_wh, &full[stage], cc * KC, wrow);
-          if (TERMS == 3) {
-            tma_load_4d(st + OFF_ALO, &tm_xl, &full[stage], cc * KC, ax, ay, n_in);
-            tma_load_2d(st + OFF_BLO, &tm_wl, &full[stage], cc * KC, wrow);
+          mbar_expect_tx(&full[stage], kBytes * (uint32_t)nsub);
+          for (int t = 0; t < nsub; ++t) {
+            const int kb = kb0 + t;
+            const int tap = kb / p.nchunks, cc = kb - tap * p.nchunks;
+            uint8_t* st = tiles + stage * STAGE + t * C::kSub;
+            const int ax = x0 + p.dx[tap], ay = y0 + p.dy[tap], wrow = p.wi[tap] * NPAD;
+            const int n_in = p.dout ? (n / p.dout) * p.din + (n % p.dout) + p.dz[tap] : n;
+            tma_load_4d(st, &tm_xh, &full[stage], cc * KC, ax, ay, n_in);
+            tma_load_2d(st + OFF_B, &tm_wh, &full[stage], cc * KC, wrow);
+            if (TERMS == 3) {
+              tma_load_4d(st + OFF_ALO, &tm_xl, &full[stage], cc * KC, ax, ay, n_in);
+              tma_load_2d(st + OFF_BLO, &tm_wl, &full[stage], cc * KC, wrow);
+            }
           }
           if (++stage == S) {
             stage = 0;
@@ -177,20 +186,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
         mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * NPAD;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += TPS) {
+          const int nsub = min(TPS, num_kb - kb0);
           mbar_wait(&full[stage], phase);
           fence_after_sync();
-          const uint32_t sa = smem_u32(tiles + stage * STAGE);
-          const uint64_t a_hi = make_smem_desc(sa, 16, C::kSbo, C::kLayout);
-          const uint64_t b_hi = make_smem_desc(sa + OFF_B, 16, C::kSbo, C::kLayout);
-          const uint64_t a_lo = make_smem_desc(sa + OFF_ALO, 16, C::kSbo, C::kLayout);
-          const uint64_t b_lo = make_smem_desc(sa + OFF_BLO, 16, C::kSbo, C::kLayout);
+          const uint32_t sa0 = smem_u32(tiles + stage * STAGE);
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k) {  // +32 B per K=16 step inside the swizzled row
-            umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) ? 1u : 0u);
-            if (TERMS == 3) {
-              umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-              umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+          for (int t = 0; t < TPS; ++t) {
+            if (t >= nsub) break;
+            const uint32_t sa = sa0 + t * C::kSub;
+            const uint64_t a_hi = make_smem_desc(sa, 16, C::kSbo, C::kLayout);
+            const uint64_t b_hi = make_smem_desc(sa + OFF_B, 16, C::kSbo, C::kLayout);
+            const uint64_t a_lo = make_smem_desc(sa + OFF_ALO, 16, C::kSbo, C::kLayout);
+            const uint64_t b_lo = make_smem_desc(sa + OFF_BLO, 16, C::kSbo, C::kLayout);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {  // +32 B per K=16 step inside the swizzled row
+              umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb0 | t | k) ? 1u : 0u);
+              if (TERMS == 3) {
+                umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+              }
             }
           }
           umma_commit(&empty[stage]);
