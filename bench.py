@@ -270,8 +270,17 @@ def run_ours(args, rank, world, local_rank):
     if top is not None:
         name, v = top
         ach = v["flops"] / (v["ms"] * 1e-3) / 1e12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(name, {}).get("bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            pass
+        mma_terms = 3 if name.startswith("tc3_") else 1
         roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " bf16 dense sustained",
+                "frac": ach / pk["tf_sust"], "traffic": traffic,
+                "peak_source": pk["src"] + " bf16 dense sustained (fp16 shares the rate)",
+                "mma_terms_per_product": mma_terms, "frac_counting_issued_mma_work": mma_terms * ach / pk["tf_sust"],
                 "share_of_step": v["ms"] / sum(x["ms"] for x in prof.values()),
                 "avg_launch_ms": v["ms"] / v["launches"]}
     whole = pairs / world * GFLOP_PER_PAIR_FULL / (ms_max * 1e-3) / 1e3  # TFLOP/s per GPU, algorithmic
