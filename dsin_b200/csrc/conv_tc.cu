@@ -143,8 +143,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
   constexpr uint32_t kBytes = (TERMS == 3 ? 2u : 1u) * (128u * KC * 2u + (uint32_t)NPAD * KC * 2u);
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (converged warp, one lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -154,20 +154,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
         for (int kb0 = 0; kb0 < num_kb; kb0 += TPS) {
           const int nsub = min(TPS, num_kb - kb0);
           mbar_wait(&empty[stage], phase ^ 1u);
-          mbar_expect_tx(&full[stage], kBytes * (uint32_t)nsub);
-          for (int t = 0; t < nsub; ++t) {
-            const int kb = kb0 + t;
-            const int tap = kb / p.nchunks, cc = kb - tap * p.nchunks;
-            uint8_t* st = tiles + stage * STAGE + t * C::kSub;
-            const int ax = x0 + p.dx[tap], ay = y0 + p.dy[tap], wrow = p.wi[tap] * NPAD;
-            const int n_in = p.dout ? (n / p.dout) * p.din + (n % p.dout) + p.dz[tap] : n;
-            tma_load_4d(st, &tm_xh, &full[stage], cc * KC, ax, ay, n_in);
-            tma_load_2d(st + OFF_B, &tm_wh, &full[stage], cc * KC, wrow);
-            if (TERMS == 3) {
-              tma_load_4d(st + OFF_ALO, &tm_xl, &full[stage], cc * KC, ax, ay, n_in);
-              tma_load_2d(st + OFF_BLO, &tm_wl, &full[stage], cc * KC, wrow);
+          if (elect_one()) {
+            mbar_expect_tx(&full[stage], kBytes * (uint32_t)nsub);
+            for (int t = 0; t < nsub; ++t) {
+              const int kb = kb0 + t;
+              const int tap = kb / p.nchunks, cc = kb - tap * p.nchunks;
+              uint8_t* st = tiles + stage * STAGE + t * C::kSub;
+              const int ax = x0 + p.dx[tap], ay = y0 + p.dy[tap], wrow = p.wi[tap] * NPAD;
+              const int n_in = p.dout ? (n / p.dout) * p.din + (n % p.dout) + p.dz[tap] : n;
+              tma_load_4d(st, &tm_xh, &full[stage], cc * KC, ax, ay, n_in);
+              tma_load_2d(st + OFF_B, &tm_wh, &full[stage], cc * KC, wrow);
+              if (TERMS == 3) {
+                tma_load_4d(st + OFF_ALO, &tm_xl, &full[stage], cc * KC, ax, ay, n_in);
+                tma_load_2d(st + OFF_BLO, &tm_wl, &full[stage], cc * KC, wrow);
+              }
             }
           }
+          __syncwarp();
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
@@ -176,8 +179,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    // The whole warp stays converged through the barrier waits; one elected lane issues (so the
+    // compiler emits plain UTCHMMA instead of a per-instruction uniformisation loop).
+    {
       constexpr uint32_t idesc = make_idesc_f16(128, NPAD, 0);
       int stage = 0, it = 0;
       uint32_t phase = 0;
@@ -190,31 +195,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
           const int nsub = min(TPS, num_kb - kb0);
           mbar_wait(&full[stage], phase);
           fence_after_sync();
-          const uint32_t sa0 = smem_u32(tiles + stage * STAGE);
+          if (elect_one()) {
+            const uint32_t sa0 = smem_u32(tiles + stage * STAGE);
 #pragma unroll
-          for (int t = 0; t < TPS; ++t) {
-            if (t >= nsub) break;
-            const uint32_t sa = sa0 + t * C::kSub;
-            const uint64_t a_hi = make_smem_desc(sa, 16, C::kSbo, C::kLayout);
-            const uint64_t b_hi = make_smem_desc(sa + OFF_B, 16, C::kSbo, C::kLayout);
-            const uint64_t a_lo = make_smem_desc(sa + OFF_ALO, 16, C::kSbo, C::kLayout);
-            const uint64_t b_lo = make_smem_desc(sa + OFF_BLO, 16, C::kSbo, C::kLayout);
+            for (int t = 0; t < TPS; ++t) {
+              if (t >= nsub) break;
+              const uint32_t sa = sa0 + t * C::kSub;
+              const uint64_t a_hi = make_smem_desc(sa, 16, C::kSbo, C::kLayout);
+              const uint64_t b_hi = make_smem_desc(sa + OFF_B, 16, C::kSbo, C::kLayout);
+              const uint64_t a_lo = make_smem_desc(sa + OFF_ALO, 16, C::kSbo, C::kLayout);
+              const uint64_t b_lo = make_smem_desc(sa + OFF_BLO, 16, C::kSbo, C::kLayout);
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k) {  // +32 B per K=16 step inside the swizzled row
-              umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb0 | t | k) ? 1u : 0u);
-              if (TERMS == 3) {
-                umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-                umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+              for (int k = 0; k < KC / 16; ++k) {  // +32 B per K=16 step inside the swizzled row
+                umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb0 | t | k) ? 1u : 0u);
+                if (TERMS == 3) {
+                  umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                  umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                }
               }
             }
+            umma_commit(&empty[stage]);
           }
-          umma_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull[acc]);
+        if (elect_one()) umma_commit(&tfull[acc]);
+        __syncwarp();
       }
     }
   } else {

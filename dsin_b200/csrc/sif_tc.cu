@@ -34,7 +34,7 @@ constexpr int STRIP_PIX = 280;          // 256 + 24 pixels (even count; 23 neede
 constexpr int B_BYTES = STRIP_PIX * 16; // 4480
 constexpr int STAGE_BYTES = A_BYTES + 5120;
 constexpr int STAGES = 4;
-constexpr int ROWS_PER_UNIT = 8;
+constexpr int ROWS_PER_UNIT = 4;  // finer work units: static round-robin imbalance < 1 %
 constexpr int TOPK = 4;
 constexpr float DELTA = 2e-3f;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * TN * 8 + 1024 /*align*/ + 512 /*barriers*/;
@@ -88,8 +88,8 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   const int units_per_img = p.ptiles * p.rgroups;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (converged warp, one lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
@@ -100,12 +100,15 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           for (int jt = 0; jt < p.jtiles; ++jt)
             for (int d = 0; d < PAIRS; ++d) {
               mbar_wait(&empty[stage], phase ^ 1u);
-              uint8_t* st = tiles + stage * STAGE_BYTES;
-              mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
+              if (elect_one()) {
+                uint8_t* st = tiles + stage * STAGE_BYTES;
+                mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
 #pragma unroll
-              for (int c = 0; c < 3; ++c)
-                tma_load_3d(st + c * 16384, &tm_q, &full[stage], d * 192 + c * 64, pt * 128, img);
-              tma_load_4d(st + A_BYTES, &tm_s, &full[stage], 0, jt * (TN / 2), i + 2 * d, img);
+                for (int c = 0; c < 3; ++c)
+                  tma_load_3d(st + c * 16384, &tm_q, &full[stage], d * 192 + c * 64, pt * 128, img);
+                tma_load_4d(st + A_BYTES, &tm_s, &full[stage], 0, jt * (TN / 2), i + 2 * d, img);
+              }
+              __syncwarp();
               if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1u;
@@ -114,8 +117,8 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (converged warp, one lane issues)
+    {
       constexpr uint32_t idesc = make_idesc_f16(128, TN, 0);
       int stage = 0, it = 0;
       uint32_t phase = 0;
@@ -131,22 +134,26 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             for (int d = 0; d < PAIRS; ++d) {
               mbar_wait(&full[stage], phase);
               fence_after_sync();
-              const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES);
-              const uint32_t sb = sa + A_BYTES;
+              if (elect_one()) {
+                const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES);
+                const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-              for (int s = 0; s < 12; ++s) {
-                // A: chunk s/4 (16 KB, SW128), K step s%4 (+32 B).  B: Toeplitz strip, pixels 2s, 2s+1.
-                const uint64_t da = make_smem_desc(sa + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024, LAYOUT_SW128);
-                const uint64_t db = make_smem_desc(sb + s * 32, 16, 128, LAYOUT_NONE);
-                umma_f16(d_tmem, da, db, idesc, (d | s) ? 1u : 0u);
+                for (int s = 0; s < 12; ++s) {
+                  // A: chunk s/4 (16 KB, SW128), K step s%4 (+32 B).  B: Toeplitz strip, pixels 2s, 2s+1.
+                  const uint64_t da = make_smem_desc(sa + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024, LAYOUT_SW128);
+                  const uint64_t db = make_smem_desc(sb + s * 32, 16, 128, LAYOUT_NONE);
+                  umma_f16(d_tmem, da, db, idesc, (d | s) ? 1u : 0u);
+                }
+                umma_commit(&empty[stage]);
               }
-              umma_commit(&empty[stage]);
+              __syncwarp();
               if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1u;
               }
             }
-            umma_commit(&tfull[acc]);
+            if (elect_one()) umma_commit(&tfull[acc]);
+            __syncwarp();
           }
       }
     }
