@@ -17,9 +17,3 @@ struct ConvTc3dArgs {
 };
 
 int conv_tc_valid3d(dsin_handle_t h, const ConvTc3dArgs& a, cudaStream_t st);
-
-// 3x3 stride-1 128->128 conv with a halo-resident activation tile (conv_halo.cu).
-int conv3x3_c128_halo(dsin_handle_t h, int n, int hh, int ww, const uint16_t* x_hi, const uint16_t* x_lo,
-                      const uint16_t* w_hi, const uint16_t* w_lo, const float* scale, const float* shift, int act,
-                      const uint16_t* r1h, const uint16_t* r1l, const uint16_t* r2h, const uint16_t* r2l,
-                      uint16_t* y_hi, uint16_t* y_lo, int terms, cudaStream_t st);
