@@ -407,3 +407,55 @@ def test_probclass_modes_match_oracle(mode):
         assert torch.allclose(sums, ref.double().reshape(2, -1).sum(1), rtol=2e-7)
     finally:
         pcm.MODE = old
+
+
+# ----------------------------------------------------------------------------- other BASELINE configs
+def test_config4_geometry_320x960_encoder_quantizer_probclass():
+    """BASELINE configs[3] geometry (320x960 crops): encoder + quantiser + probclass vs the oracle."""
+    Wt = calibrated_weights(0)
+    ae = make_ae(320, 960, Wt)
+    x, _ = synth.make_batch(2, 320, 960, seed=4000)
+    enc = ae.ae_imgcomp.encode(_dev(x))
+    n_mism, bad, total = symbol_report(enc.symbols.cpu(), x, Wt)
+    assert bad == 0 and n_mism <= max(2, total // 20000), (n_mism, bad, total)
+    enc_ref = O.encode(torch.tensor(x), Wt)
+    ref_bits = O.probclass_bitcost(enc_ref.qbar, enc_ref.symbols, Wt)
+    bc = ae.pc_imgcomp.bitcost(enc_ref.qbar.cuda().contiguous(), enc_ref.symbols.cuda(), False,
+                               pad_value=ae.pc_imgcomp.auto_pad_value(ae.ae_imgcomp))
+    bpp_gpu = float(bc._dsin_sum.sum().item()) / (2 * 320 * 960)
+    bpp_ref = float(O.bitcost_to_bpp(ref_bits, 2 * 320 * 960))
+    assert abs(bpp_gpu - bpp_ref) <= 1e-5, (bpp_gpu, bpp_ref)
+
+
+def test_config3_sifinder_isolated_batch():
+    """BASELINE configs[2] (SI-Finder in isolation) at a reduced batch: every pair of the batch gets the
+    same (row, col) as when it is processed alone (pairs are independent)."""
+    from dsin_b200.siFinder import match_images
+    x, y = _sif_case(320, 1224, 60, n=3)
+    args = lambda sl: (_nhwc(_dev(x[sl])), _nhwc(_dev(y[sl])), _nhwc(_dev(y[sl])), 20, 24, True)  # noqa: E731
+    _, _, _, row, col, best = match_images(*args(slice(0, 3)))
+    for n in range(3):
+        _, _, _, r1, c1, b1 = match_images(*args(slice(n, n + 1)))
+        assert torch.equal(row[n], r1[0]) and torch.equal(col[n], c1[0]) and torch.equal(best[n], b1[0])
+
+
+def test_ae_only_mode_and_error_paths():
+    Wt = calibrated_weights(0)
+    from parity_utils import configs
+    from dsin_b200.AE import AE
+    from dsin_b200.decoder_imgcomp import decoder
+    from dsin_b200.encoder_imgcomp import encoder
+    from dsin_b200.siFinder import siFinder
+    from dsin_b200.siFull_img import SI_full_img
+    from dsin_b200.siNet import siNet
+    ae_config, pc_config = configs(80, 144)
+    ae_config.AE_only = True
+    ae = AE(ae_config, pc_config, encoder, decoder, siFinder, SI_full_img, siNet, "", weights=Wt)
+    x, y = synth.make_batch(1, 80, 144, seed=9)
+    y_dec, y_syn, x_dec, x_with_si, bpp = ae.siNet_get_reconstructed(x, y)
+    assert float(np.abs(x_with_si).max()) == 0.0 and np.isfinite(x_dec).all() and bpp > 0
+    with pytest.raises(NotImplementedError):
+        ae.siNet_update(x, y)
+    ae_config.arch = "nope"
+    with pytest.raises(KeyError):
+        AE(ae_config, pc_config, encoder, decoder, siFinder, SI_full_img, siNet, "", weights=Wt)
