@@ -19,6 +19,7 @@
 //   terms = 1:  hi*hi only             -> fp16 operands (fast mode)
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
 // warps 2-5 = epilogue (TMEM -> registers -> scale/shift/act/residual/post -> global).
+#include <stdlib.h>
 #include "tc_common.cuh"
 #include "conv_tc.cuh"
 
@@ -504,6 +505,25 @@ extern "C" int dsin_conv2d_tc(dsin_handle_t h, const dsin_conv_desc_t* d, int te
       }
     p.tiles_w = (p.GW + BW - 1) / BW; p.tiles_h = (p.GH + BH - 1) / BH;
     p.total_tiles = d->n * p.tiles_w * p.tiles_h;
+    static const bool use_pairs = getenv("DSIN_NO_CTA2") == nullptr;
+    if (use_pairs && KC == 64 && NPAD == 128 && d->cout == 128 && y_hi && !y_f32 && d->post == DSIN_POST_NONE &&
+        d->act != DSIN_ACT_LRELU02 && p.total_tiles >= 2) {
+      // CTA-pair kernel: each CTA of a pair loads half of the weight slab (64 couts)
+      CUtensorMap wh2, wl2;
+      const uint32_t wb2[2] = {64, 64};
+      if (!encode_tmap(&wh2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w_hi, wd, wsb, wb2, sw) ||
+          !encode_tmap(&wl2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w_lo ? w_lo : w_hi, wd, wsb, wb2, sw))
+        return dsin_fail(h, DSIN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", __func__);
+      ConvTc2Args a;
+      memset(&a, 0, sizeof(a));
+      a.scale = scale; a.shift = shift;
+      a.r1h = p.r1h; a.r1l = p.r1l; a.r2h = p.r2h; a.r2l = p.r2l; a.yh = p.yh; a.yl = p.yl;
+      a.n = d->n; a.OH = p.OH; a.OW = p.OW; a.in_step = step; a.act = d->act;
+      a.ntaps = p.ntaps; a.nchunks = p.nchunks;
+      a.tiles_w = p.tiles_w; a.tiles_h = p.tiles_h; a.total_tiles = p.total_tiles;
+      for (int t = 0; t < p.ntaps; ++t) { a.dy[t] = p.dy[t]; a.dx[t] = p.dx[t]; a.wi[t] = p.wi[t]; }
+      return conv_tc2_launch(h, terms, xh, xl, wh2, wl2, a, st);
+    }
     return launch(p);
   }
   // stride-2 transposed conv, TF SAME: out[o] = sum_{i,k: 2i + k - b = o} in[i] w[k]; phase (py,px) of the

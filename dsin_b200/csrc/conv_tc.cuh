@@ -1,5 +1,6 @@
 // Internal (non-ABI) entry of the generic tensor-core conv for 3-D VALID convolutions.
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 
 struct ConvTc3dArgs {
@@ -17,3 +18,16 @@ struct ConvTc3dArgs {
 };
 
 int conv_tc_valid3d(dsin_handle_t h, const ConvTc3dArgs& a, cudaStream_t st);
+
+// CTA-pair (cta_group::2) kernel for the 128-cout, 64-channel-block convolutions (conv_tc2.cu).
+struct ConvTc2Args {
+  const float* scale;
+  const float* shift;
+  const __half *r1h, *r1l, *r2h, *r2l;
+  __half *yh, *yl;
+  int n, OH, OW, in_step, act, ntaps, nchunks;
+  int tiles_w, tiles_h, total_tiles;
+  short dy[25], dx[25], wi[25];
+};
+int conv_tc2_launch(dsin_handle_t h, int terms, const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh,
+                    const CUtensorMap& wl, const ConvTc2Args& p, cudaStream_t st);
