@@ -7,12 +7,13 @@
 //            running reduction over TMEM columns, no cross-thread traffic);
 //   N axis = 256 consecutive positions of one correlation row.
 // The position operand is Toeplitz (window j+1 = window j shifted by one pixel).  It is fed ZERO-COPY:
-// the search image is stored as 16-byte "pixels" S[y][x] = fp16 {r(y,x,0..2), r(y+1,x,0..2), 0, 0};
-// one TMA box brings a strip of 280 such pixels into shared memory, and a no-swizzle K-major UMMA
-// descriptor with LBO = 16 B (next K chunk = next pixel) and SBO = 128 B (next 8 positions) makes row n
-// of the operand start 16*n bytes into the strip -- overlapping windows, no im2col.  One K=16 MMA step
-// consumes two pixels x two image rows; a patch-row pair is 24 px = 12 steps; 10 pairs per patch.
-// (6 of 8 K slots carry data: 75 % K efficiency, the price of the 16-byte row pitch.)
+// for every correlation row i the 60 values of a window COLUMN (20 rows x 3 channels at pixel x) are
+// stored as 8 "layers" of 16-byte pixels, S_l[i][x] = fp16 {v[8l..8l+7]}, v[k] = r(i + k/3, x, k%3)
+// (the last layer has 4 zero slots: 60 of 64 K slots carry data).  One TMA box brings a strip of 280
+// such pixels into shared memory, and a no-swizzle K-major UMMA descriptor with LBO = 16 B (next K chunk
+// = next pixel) and SBO = 128 B (next 8 positions) makes row n of the operand start 16*n bytes into the
+// strip -- overlapping windows, no im2col.  One K=16 MMA step consumes two pixels of one layer; a layer
+// is 24 px = 12 steps; 8 layers per patch (96 MMAs of 128x256x16 per tile).
 // Patches are pre-centred per patch (q - mean_q) before the fp16 rounding, which removes the large
 // cancellation in the Pearson numerator; the coarse score error is ~1e-4.  Each work unit (image,
 // patch tile, 8 correlation rows) keeps the 4 best coarse candidates per patch; a second kernel rescored
@@ -26,9 +27,10 @@ using namespace tc;
 namespace {
 
 constexpr int TN = 256;                 // positions per tile
-constexpr int PAIRS = 10;               // patch-row pairs (ph = 20)
+constexpr int PAIRS = 8;                // K layers: the 60 values of a window column (20 rows x 3 ch) in 8 x 8 slots
+constexpr int PHX = 20;                 // patch height
 constexpr int PWX = 24;                 // patch width in pixels
-constexpr int KQ = PAIRS * PWX * 8;     // packed K per patch (1920 fp16)
+constexpr int KQ = PAIRS * PWX * 8;     // packed K per patch (1536 fp16, 1440 of them data)
 constexpr int A_BYTES = 3 * 128 * 128;  // three [128 patches x 64 k] SW128 tiles per pair = 48 KB
 constexpr int STRIP_PIX = 280;          // 256 + 24 pixels (even count; 23 needed)
 constexpr int B_BYTES = STRIP_PIX * 16; // 4480
@@ -106,7 +108,7 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
                   tma_load_3d(st + c * 16384, &tm_q, &full[stage], d * 192 + c * 64, pt * 128, img);
-                tma_load_4d(st + A_BYTES, &tm_s, &full[stage], 0, jt * (TN / 2), i + 2 * d, img);
+                tma_load_4d(st + A_BYTES, &tm_s, &full[stage], 0, jt * (TN / 2), i, img * PAIRS + d);
               }
               __syncwarp();
               if (++stage == STAGES) {
@@ -267,17 +269,19 @@ __global__ void sif_pack_q_kernel(const float* __restrict__ q, const float* __re
   const float xm = pstat[wid * 4 + 2];
   float s16 = 0.f;
   __half* out = q2 + wid * KQ;
-  for (int e = lane; e < (ph / 2) * pw; e += 32) {  // (pair d, pixel px)
-    const int d = e / pw, px = e % pw;
+  for (int e = lane; e < PAIRS * pw; e += 32) {  // (layer l, pixel px)
+    const int l = e / pw, px = e % pw;
     __half hv[8];
 #pragma unroll
-    for (int t = 0; t < 6; ++t) {
-      const int dy = 2 * d + t / 3, c = t % 3;
-      __half hq = __float2half_rn(qp[(dy * pw + px) * 3 + c] - xm);
+    for (int t = 0; t < 8; ++t) {
+      const int k = 8 * l + t;  // value index within the window column: k = dy*3 + c
+      __half hq = __float2half_rn(0.f);
+      if (k < ph * 3) {
+        hq = __float2half_rn(qp[((k / 3) * pw + px) * 3 + (k % 3)] - xm);
+        s16 += __half2float(hq);
+      }
       hv[t] = hq;
-      s16 += __half2float(hq);
     }
-    hv[6] = hv[7] = __float2half_rn(0.f);
     *reinterpret_cast<uint4*>(out + (size_t)e * 8) = *reinterpret_cast<const uint4*>(hv);
   }
   for (int o = 16; o > 0; o >>= 1) s16 += __shfl_xor_sync(0xffffffffu, s16, o);
@@ -290,24 +294,26 @@ __global__ void sif_pack_q_kernel(const float* __restrict__ q, const float* __re
   }
 }
 
-// S[y][x] = {r(y,x,0..2), r(y+1,x,0..2), 0, 0} as fp16, y in [0, hh-1)
+// S_l[i][x] = fp16 {v[8l..8l+7]}, v[k] = r(i + k/3, x, k%3), for every correlation row i in [0, hp)
 __global__ void sif_pack_strip_kernel(const float* __restrict__ r, __half* __restrict__ s, int n, int hh,
-                                      int ww) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)n * (hh - 1) * ww) return;
+                                      int ww, int ph) {
+  const int hp = hh - ph + 1;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (img, layer, i, x)
+  if (idx >= (int64_t)n * PAIRS * hp * ww) return;
   const int x = (int)(idx % ww);
-  const int64_t t = idx / ww;
-  const int y = (int)(t % (hh - 1));
-  const int img = (int)(t / (hh - 1));
-  const float* a = r + (((int64_t)img * hh + y) * ww + x) * 3;
-  const float* b = a + (int64_t)ww * 3;
+  int64_t t = idx / ww;
+  const int i = (int)(t % hp);
+  t /= hp;
+  const int l = (int)(t % PAIRS);
+  const int img = (int)(t / PAIRS);
   __half hv[8];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    hv[c] = __float2half_rn(a[c]);
-    hv[3 + c] = __float2half_rn(b[c]);
+  for (int q8 = 0; q8 < 8; ++q8) {
+    const int k = 8 * l + q8;
+    float v = 0.f;
+    if (k < ph * 3) v = r[(((int64_t)img * hh + i + k / 3) * ww + x) * 3 + (k % 3)];
+    hv[q8] = __float2half_rn(v);
   }
-  hv[6] = hv[7] = __float2half_rn(0.f);
   reinterpret_cast<uint4*>(s)[idx] = *reinterpret_cast<const uint4*>(hv);
 }
 
@@ -369,7 +375,7 @@ Layout make_layout(int n, int hh, int ww, int ph, int pw) {
   auto up = [](int64_t v) { return (v + 1023) / 1024 * 1024; };
   L.q2 = 0;
   L.strip = up((int64_t)n * P * KQ * 2);
-  L.pinfo = L.strip + up((int64_t)n * (hh - 1) * ww * 16);
+  L.pinfo = L.strip + up((int64_t)n * PAIRS * (hh - ph + 1) * ww * 16);
   L.cand = L.pinfo + up((int64_t)n * P * 16);
   L.total = L.cand + up((int64_t)n * P * L.ncand * 8);
   return L;
@@ -384,7 +390,7 @@ int64_t sif_tc_workspace_bytes(int n, int hh, int ww, int ph, int pw, int method
 
 int sif_tc_match(dsin_handle_t h, const float* q, const float* r, const float* pstat, const float* ystat, int n,
                  int hh, int ww, int ph, int pw, int use_mask, unsigned long long* keys, void* ws, cudaStream_t st) {
-  if (ph != 2 * PAIRS || pw != PWX)
+  if (ph != PHX || pw != PWX)
     return dsin_fail(h, DSIN_ERR_UNSUPPORTED, "%s: tensor-core SI-Finder is built for 20x24 patches", __func__);
   if (ww % 2 != 0) return dsin_fail(h, DSIN_ERR_UNSUPPORTED, "%s: image width must be even", __func__);
   const int P = (hh / ph) * (ww / pw), hp = hh - ph + 1, wp = ww - pw + 1;
@@ -398,16 +404,16 @@ int sif_tc_match(dsin_handle_t h, const float* q, const float* r, const float* p
   const int64_t np = (int64_t)n * P;
   sif_pack_q_kernel<<<(unsigned)((np * 32 + 255) / 256), 256, 0, st>>>(q, pstat, q2, pinfo, n, P, ph, pw, hh, ww);
   DSIN_LAUNCHED(h);
-  const int64_t ns = (int64_t)n * (hh - 1) * ww;
-  sif_pack_strip_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(r, strip, n, hh, ww);
+  const int64_t ns = (int64_t)n * PAIRS * hp * ww;
+  sif_pack_strip_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(r, strip, n, hh, ww, ph);
   DSIN_LAUNCHED(h);
 
   CUtensorMap tm_q, tm_s;
   const uint64_t qd[3] = {(uint64_t)KQ, (uint64_t)P, (uint64_t)n};
   const uint64_t qs[2] = {(uint64_t)KQ * 2, (uint64_t)P * KQ * 2};
   const uint32_t qb[3] = {64, 128, 1};
-  const uint64_t sd[4] = {16, (uint64_t)ww / 2, (uint64_t)(hh - 1), (uint64_t)n};
-  const uint64_t ss[3] = {32, (uint64_t)ww * 16, (uint64_t)(hh - 1) * ww * 16};
+  const uint64_t sd[4] = {16, (uint64_t)ww / 2, (uint64_t)hp, (uint64_t)n * PAIRS};
+  const uint64_t ss[3] = {32, (uint64_t)ww * 16, (uint64_t)hp * ww * 16};
   const uint32_t sb[4] = {16, STRIP_PIX / 2, 1, 1};
   if (!encode_tmap(&tm_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, q2, qd, qs, qb, CU_TENSOR_MAP_SWIZZLE_128B) ||
       !encode_tmap(&tm_s, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, strip, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_NONE))
