@@ -34,6 +34,30 @@ __global__ void concat_normalize_kernel(const float* __restrict__ a, const float
   }
 }
 
+// concat([normalize(x_dec), normalize(y_syn)]) written as a 32-channel split-fp16 tensor (channels 6..31 = 0)
+// so that the first SI-Net layer can run on the 32-channel tensor-core kernel.
+__global__ void concat_normalize_split32_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                __half* __restrict__ hi, __half* __restrict__ lo, int64_t npix) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npix * 4) return;  // 4 x 16-byte pieces (8 channels) per pixel
+  const int64_t pix = idx >> 2;
+  const int piece = (int)(idx & 3);
+  __half h[8], l[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) h[e] = l[e] = __float2half_rn(0.f);
+  if (piece == 0) {
+#pragma unroll
+    for (int ch = 0; ch < 6; ++ch) {
+      const float raw = ch < 3 ? a[pix * 3 + ch] : b[pix * 3 + ch - 3];
+      const float v = __fdiv_rn(__fsub_rn(raw, dsin_mean(ch % 3)), dsin_std(ch % 3));
+      h[ch] = __float2half_rn(v);
+      l[ch] = __float2half_rn(v - __half2float(h[ch]));
+    }
+  }
+  reinterpret_cast<uint4*>(hi)[idx] = *reinterpret_cast<const uint4*>(h);
+  reinterpret_cast<uint4*>(lo)[idx] = *reinterpret_cast<const uint4*>(l);
+}
+
 __global__ void f32_to_split_kernel(const float* __restrict__ x, __half* __restrict__ hi,
                                     __half* __restrict__ lo, int64_t count) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -78,6 +102,16 @@ int dsin_concat_normalize(dsin_handle_t h, const float* a, const float* b, float
   DSIN_REQUIRE(h, a && b && out && n > 0, "bad argument");
   int64_t tot = (int64_t)n * hh * ww;
   concat_normalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, tot);
+  DSIN_LAUNCHED(h);
+  return DSIN_OK;
+}
+
+int dsin_concat_normalize_split32(dsin_handle_t h, const float* a, const float* b, uint16_t* hi, uint16_t* lo, int n,
+                                  int hh, int ww, void* stream) {
+  DSIN_REQUIRE(h, a && b && hi && lo && n > 0, "bad argument");
+  int64_t tot = (int64_t)n * hh * ww;
+  concat_normalize_split32_kernel<<<(unsigned)((tot * 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      a, b, (__half*)hi, (__half*)lo, tot);
   DSIN_LAUNCHED(h);
   return DSIN_OK;
 }

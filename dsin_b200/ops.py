@@ -38,6 +38,16 @@ def _chk(t, dtype=torch.float32):
     return t
 
 
+def concat_normalize_split32(xdec_nhwc, ysyn_nhwc):
+    h = handle()
+    n, hh, ww, _ = xdec_nhwc.shape
+    hi = torch.empty((n, hh, ww, 32), dtype=torch.float16, device=xdec_nhwc.device)
+    lo = torch.empty((n, hh, ww, 32), dtype=torch.float16, device=xdec_nhwc.device)
+    h.check(h.lib.dsin_concat_normalize_split32(h.ptr, _p(_chk(xdec_nhwc)), _p(_chk(ysyn_nhwc)), _p(hi), _p(lo), n,
+                                                hh, ww, _stream()))
+    return hi, lo
+
+
 class _Profiler(object):
     """Optional per-kernel CUDA-event timing (bench.py's roofline): when enabled every wrapped
     launch is bracketed by events on the launching stream and tagged with its algorithmic FLOPs."""

@@ -38,6 +38,12 @@ class SiNet(object):
                                     device=self.device))
         self.layers = layers
         self._tc = None
+        # first layer with its 6 input channels zero-padded to 32 (tensor-core form)
+        w1 = np.zeros((3, 3, 32, 32), dtype=np.float32)
+        w1[:, :, :6, :] = W[S + "g_conv1/weights"]
+        self._first_padded = ops.ConvLayer(w1, None, W[S + "g_conv1/biases"], dilation=1, act=ops.ACT_LRELU02,
+                                           device=self.device)
+        self._tc_first = None
 
     def _run(self, net, post):
         n, hh, ww, _ = net.shape
@@ -58,6 +64,21 @@ class SiNet(object):
         return ops.nhwc_to_nchw(self._run(net, ops.POST_NONE))
 
     def fused(self, x_dec_nhwc, y_syn_nhwc):
+        n, hh, ww, _ = x_dec_nhwc.shape
+        if MODE in ("tc3", "tc1") and hh >= 8 and ww >= 16:
+            terms = 3 if MODE == "tc3" else 1
+            if self._tc is None:
+                self._tc = [ops.ConvTC(layer) for layer in self.layers[1:]]
+            if self._tc_first is None:
+                self._tc_first = ops.ConvTC(self._first_padded)
+            cur = ops.concat_normalize_split32(x_dec_nhwc, y_syn_nhwc)
+            cur = ops.conv_tc(cur, self._tc_first, terms=terms)
+            for tcl in self._tc[:-1]:
+                cur = ops.conv_tc(cur, tcl, terms=terms)
+            out_nhwc = ops.conv_tc(cur, self._tc[-1], terms=terms, out_f32=True, post=ops.POST_DENORM)
+            out = ops.nhwc_to_nchw(out_nhwc)
+            out._dsin_nhwc = out_nhwc
+            return out
         net = ops.concat_normalize(x_dec_nhwc, y_syn_nhwc)
         out_nhwc = self._run(net, ops.POST_DENORM)
         out = ops.nhwc_to_nchw(out_nhwc)

@@ -51,6 +51,11 @@ int dsin_nhwc_to_nchw(dsin_handle_t h, const float* x_nhwc, float* y_nchw, int n
 int dsin_concat_normalize(dsin_handle_t h, const float* xdec_nhwc, const float* ysyn_nhwc,
                           float* out_nhwc6, int n, int hh, int ww, void* stream);
 
+/* Same concat, written as a 32-channel split-fp16 NHWC tensor (channels 6..31 zero) for the tensor-core
+ * SI-Net path (the first layer's weights are zero-padded to 32 input channels by the caller). */
+int dsin_concat_normalize_split32(dsin_handle_t h, const float* xdec_nhwc, const float* ysyn_nhwc,
+                                  uint16_t* hi, uint16_t* lo, int n, int hh, int ww, void* stream);
+
 /* ---- K1/K2/K8: convolution + folded BN / bias + activation + residual adds --------------
  * Replaces slim.conv2d / slim.conv2d_transpose + slim.batch_norm + ReLU + the skip adds
  * (src/autoencoder_imgcomp.py:223-266,275-288) and the siNet convs (src/siNet.py:31-40).
