@@ -41,7 +41,7 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 }
 
 template <int TERMS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
                 const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
                 const __grid_constant__ ConvTc2Args p) {
@@ -71,7 +71,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);  // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+      mbar_init(&tempty[i], 16);  // 8 epilogue warps x 2 CTAs (only the leader's copy is used)
     }
     fence_barrier_init();
     prefetch_tmap(&tm_xh);
@@ -168,10 +168,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps 2..5 (both CTAs, own TMEM)
+    // ------------------------------------------------------------ epilogue warps 2..9 (both CTAs, own TMEM)
+    // Two warps per TMEM lane quarter, 64 columns each; the residual loads of chunk c+1 (and of the tile's
+    // first chunk, before the accumulator-full wait) are in flight while chunk c is processed.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int hl = row >> 4, wl = row & 15;
+    const bool has_r1 = p.r1h != nullptr, has_r2 = p.r2h != nullptr;
+    const bool has_r1l = p.r1l != nullptr, has_r2l = p.r2l != nullptr;
     int it = 0;
     for (int pi = cid; pi < pairs; pi += nclusters, ++it) {
       const int acc = it & 1;
@@ -183,77 +188,94 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
       const int oy = th * BH + hl, ox = tw * BW + wl;
       const bool valid = tvalid && oy < p.OH && ox < p.OW;
       const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
-      mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u);
-      fence_after_sync();
-#pragma unroll 1
-      for (int chunk = 0; chunk < 8; ++chunk) {
-        const int c0 = chunk * 16;
-        const size_t off = pix * 128 + c0;
-        uint4 r[8];
-        if (valid) {
-          if (p.r1h) {
-            r[0] = __ldg(reinterpret_cast<const uint4*>(p.r1h + off));
-            r[1] = __ldg(reinterpret_cast<const uint4*>(p.r1h + off) + 1);
-            if (p.r1l) {
-              r[2] = __ldg(reinterpret_cast<const uint4*>(p.r1l + off));
-              r[3] = __ldg(reinterpret_cast<const uint4*>(p.r1l + off) + 1);
-            }
-          }
-          if (p.r2h) {
-            r[4] = __ldg(reinterpret_cast<const uint4*>(p.r2h + off));
-            r[5] = __ldg(reinterpret_cast<const uint4*>(p.r2h + off) + 1);
-            if (p.r2l) {
-              r[6] = __ldg(reinterpret_cast<const uint4*>(p.r2l + off));
-              r[7] = __ldg(reinterpret_cast<const uint4*>(p.r2l + off) + 1);
-            }
+      uint4 ra[8], rb[8];
+      auto load_res = [&](int chunk, uint4 (&dst)[8]) {
+        const size_t off = pix * 128 + chunk * 16;
+        if (has_r1) {
+          dst[0] = __ldg(reinterpret_cast<const uint4*>(p.r1h + off));
+          dst[1] = __ldg(reinterpret_cast<const uint4*>(p.r1h + off) + 1);
+          if (has_r1l) {
+            dst[2] = __ldg(reinterpret_cast<const uint4*>(p.r1l + off));
+            dst[3] = __ldg(reinterpret_cast<const uint4*>(p.r1l + off) + 1);
           }
         }
+        if (has_r2) {
+          dst[4] = __ldg(reinterpret_cast<const uint4*>(p.r2h + off));
+          dst[5] = __ldg(reinterpret_cast<const uint4*>(p.r2h + off) + 1);
+          if (has_r2l) {
+            dst[6] = __ldg(reinterpret_cast<const uint4*>(p.r2l + off));
+            dst[7] = __ldg(reinterpret_cast<const uint4*>(p.r2l + off) + 1);
+          }
+        }
+      };
+      auto process = [&](int chunk, const uint4 (&rr)[8]) {
+        const int c0 = chunk * 16;
         uint32_t v[16];
         tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + c0), v);
         tmem_ld_wait();
-        if (valid) {
-          float f[16];
+        if (!valid) return;
+        float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float t = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), s_scale[c0 + j]), s_shift[c0 + j]);
-            f[j] = p.act == DSIN_ACT_RELU ? fmaxf(t, 0.f) : t;
-          }
-#pragma unroll
-          for (int rr = 0; rr < 2; ++rr) {
-            const bool on = rr == 0 ? p.r1h != nullptr : p.r2h != nullptr;
-            const bool lo_on = rr == 0 ? p.r1l != nullptr : p.r2l != nullptr;
-            if (on) {
-#pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                float a[8], b[8];
-                unpack8(r[rr * 4 + g], a);
-                if (lo_on) {
-                  unpack8(r[rr * 4 + 2 + g], b);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) a[e] = __fadd_rn(a[e], b[e]);
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[g * 8 + e] = __fadd_rn(f[g * 8 + e], a[e]);
-              }
-            }
-          }
+        for (int j = 0; j < 16; ++j) {
+          float t = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), s_scale[c0 + j]), s_shift[c0 + j]);
+          f[j] = p.act == DSIN_ACT_RELU ? fmaxf(t, 0.f) : t;
+        }
+        if (has_r1) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
-            uint4 uh, ul;
-            __half2* hh = reinterpret_cast<__half2*>(&uh);
-            __half2* ll = reinterpret_cast<__half2*>(&ul);
+            float a[8], b[8];
+            unpack8(rr[g], a);
+            if (has_r1l) {
+              unpack8(rr[2 + g], b);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float x0 = f[g * 8 + 2 * e], x1 = f[g * 8 + 2 * e + 1];
-              __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-              hh[e] = __halves2half2(h0, h1);
-              ll[e] = __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+              for (int e = 0; e < 8; ++e) a[e] = __fadd_rn(a[e], b[e]);
             }
-            reinterpret_cast<uint4*>(p.yh + off)[g] = uh;
-            if (p.yl) reinterpret_cast<uint4*>(p.yl + off)[g] = ul;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[g * 8 + e] = __fadd_rn(f[g * 8 + e], a[e]);
           }
         }
-      }
+        if (has_r2) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float a[8], b[8];
+            unpack8(rr[4 + g], a);
+            if (has_r2l) {
+              unpack8(rr[6 + g], b);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a[e] = __fadd_rn(a[e], b[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[g * 8 + e] = __fadd_rn(f[g * 8 + e], a[e]);
+          }
+        }
+        const size_t off = pix * 128 + c0;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint4 uh, ul;
+          __half2* hh = reinterpret_cast<__half2*>(&uh);
+          __half2* ll = reinterpret_cast<__half2*>(&ul);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x0 = f[g * 8 + 2 * e], x1 = f[g * 8 + 2 * e + 1];
+            __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+            hh[e] = __halves2half2(h0, h1);
+            ll[e] = __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+          }
+          reinterpret_cast<uint4*>(p.yh + off)[g] = uh;
+          if (p.yl) reinterpret_cast<uint4*>(p.yl + off)[g] = ul;
+        }
+      };
+      const int cb = half * 4;
+      if (valid) load_res(cb, ra);
+      mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u);
+      fence_after_sync();
+      if (valid) load_res(cb + 1, rb);
+      process(cb, ra);
+      if (valid) load_res(cb + 2, ra);
+      process(cb + 1, rb);
+      if (valid) load_res(cb + 3, rb);
+      process(cb + 2, ra);
+      process(cb + 3, rb);
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty[acc], 0);  // the leader's accumulator-empty barrier
@@ -282,7 +304,7 @@ int launch2(dsin_handle_t h, const CUtensorMap& xh, const CUtensorMap& xl, const
   const int pairs = (p.total_tiles + 1) / 2;
   int clusters = h->sm_count / 2;
   if (clusters > pairs) clusters = pairs;
-  conv_tc2_kernel<TERMS><<<2 * clusters, 192, C::kSmem, st>>>(xh, xl, wh, wl, p);
+  conv_tc2_kernel<TERMS><<<2 * clusters, 320, C::kSmem, st>>>(xh, xl, wh, wl, p);
   DSIN_LAUNCHED(h);
   return DSIN_OK;
 }
