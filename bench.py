@@ -27,6 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 H, W = 320, 1224
+if os.environ.get("DSIN_BENCH_HW"):  # test hook only (tests/test_bench_contract.py): shrink the geometry
+    H, W = (int(v) for v in os.environ["DSIN_BENCH_HW"].split("x"))
 PH, PW = 20, 24
 GFLOP_PER_PAIR_FULL = 1893.9  # SURVEY App. B / BASELINE.md section 4
 METRIC = "Mpixels/s decode (320x1224 pairs)"

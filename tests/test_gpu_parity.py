@@ -459,3 +459,26 @@ def test_ae_only_mode_and_error_paths():
     ae_config.arch = "nope"
     with pytest.raises(KeyError):
         AE(ae_config, pc_config, encoder, decoder, siFinder, SI_full_img, siNet, "", weights=Wt)
+
+
+def test_cabi_error_codes_and_messages():
+    """Bad arguments come back as negative codes with a message; nothing is launched."""
+    import ctypes as C
+    from dsin_b200 import _lib, ops
+    h = ops.handle()
+    lib = h.lib
+    before = h.launch_count()
+    d = _lib.ConvDesc(1, 8, 16, 3, 3, 3, 3, 3, 1, 0, 0, 0)  # stride 3 is not supported
+    x = torch.zeros(1, 8, 16, 3, device="cuda")
+    rc = lib.dsin_conv2d(h.ptr, C.byref(d), C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()), None, None, None,
+                         None, C.c_void_p(x.data_ptr()), None)
+    assert rc == -1 and b"stride" in lib.dsin_last_error(h.ptr)
+    rc = lib.dsin_heatmap_quantize(h.ptr, None, None, 6, 1, 1, 1, 1, None, None, None, None)
+    assert rc == -1
+    rc = lib.dsin_sif_prepare(h.ptr, C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()), 1, 30, 50, 20, 24,
+                              C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()),
+                              C.c_void_p(x.data_ptr()), None)
+    assert rc == -1 and b"tile" in lib.dsin_last_error(h.ptr)
+    assert h.launch_count() == before
+    with pytest.raises(RuntimeError):
+        h.check(rc)
