@@ -18,7 +18,8 @@ class DsinLibraryError(RuntimeError):
 
 class ConvDesc(C.Structure):
     _fields_ = [(k, C.c_int) for k in
-                ("n", "h", "w", "cin", "cout", "kh", "kw", "stride", "dilation", "transposed", "act", "post")]
+                ("n", "h", "w", "cin", "cout", "kh", "kw", "stride", "dilation", "transposed", "act", "post",
+                 "dilation_x")]
 
 
 ACT_NONE, ACT_RELU, ACT_LRELU02 = 0, 1, 2

@@ -149,6 +149,7 @@ extern "C" int dsin_conv2d(dsin_handle_t h, const dsin_conv_desc_t* d, const flo
   DSIN_REQUIRE(h, d->dilation >= 1 && (d->dilation == 1 || d->stride == 1), "bad dilation");
   DSIN_REQUIRE(h, !d->transposed || (d->stride == 2 && d->dilation == 1), "transposed conv is stride 2");
   DSIN_REQUIRE(h, d->post == DSIN_POST_NONE || d->cout == 3, "denormalisation needs cout == 3");
+  DSIN_REQUIRE(h, d->dilation_x == 0 || d->dilation_x == d->dilation, "anisotropic dilation: tensor-core path only");
   ConvP p;
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.res1 = res1; p.res2 = res2; p.y = y;
   p.n = d->n; p.h = d->h; p.w_ = d->w; p.cin = d->cin; p.cout = d->cout; p.kh = d->kh; p.kw = d->kw;

@@ -494,13 +494,14 @@ extern "C" int dsin_conv2d_tc(dsin_handle_t h, const dsin_conv_desc_t* d, int te
   if (!d->transposed) {
     p.OH = (d->h + d->stride - 1) / d->stride; p.OW = (d->w + d->stride - 1) / d->stride;
     p.GH = p.OH; p.GW = p.OW; p.os = 1; p.py = 0; p.px = 0;
+    const int dil_x = d->dilation_x > 0 ? d->dilation_x : d->dilation;
     const int pt = dsin_same_pad_before(d->h, k, d->stride, d->dilation);
-    const int pl = dsin_same_pad_before(d->w, k, d->stride, d->dilation);
+    const int pl = dsin_same_pad_before(d->w, k, d->stride, dil_x);
     p.ntaps = k * k;
     for (int ky = 0; ky < k; ++ky)
       for (int kx = 0; kx < k; ++kx) {
         p.dy[ky * k + kx] = (short)(ky * d->dilation - pt);
-        p.dx[ky * k + kx] = (short)(kx * d->dilation - pl);
+        p.dx[ky * k + kx] = (short)(kx * dil_x - pl);
         p.wi[ky * k + kx] = (short)(ky * k + kx);
       }
     p.tiles_w = (p.GW + BW - 1) / BW; p.tiles_h = (p.GH + BH - 1) / BH;
@@ -557,7 +558,7 @@ extern "C" int dsin_conv3x3_c128_tc(dsin_handle_t h, int n, int hh, int ww, cons
                                     const float* scale, const float* shift, int act, const uint16_t* res1_hi,
                                     const uint16_t* res1_lo, const uint16_t* res2_hi, const uint16_t* res2_lo,
                                     uint16_t* y_hi, uint16_t* y_lo, int terms, void* stream) {
-  dsin_conv_desc_t d = {n, hh, ww, 128, 128, 3, 3, 1, 1, 0, act, DSIN_POST_NONE};
+  dsin_conv_desc_t d = {n, hh, ww, 128, 128, 3, 3, 1, 1, 0, act, DSIN_POST_NONE, 0};
   DSIN_REQUIRE(h, y_hi && (terms == 1 || y_lo), "null output");
   return dsin_conv2d_tc(h, &d, terms, x_hi, x_lo, w_hi, w_lo, scale, shift, res1_hi, res1_lo, res2_hi, res2_lo, y_hi,
                         y_lo, nullptr, stream);

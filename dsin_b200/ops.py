@@ -131,6 +131,7 @@ class ConvLayer(object):
         self.scale = None if scale is None else torch.from_numpy(np.ascontiguousarray(scale, np.float32)).to(device)
         self.shift = None if shift is None else torch.from_numpy(np.ascontiguousarray(shift, np.float32)).to(device)
         self.stride, self.dilation, self.transposed, self.act, self.post = stride, dilation, transposed, act, post
+        self.dilation_x = 0  # tensor-core path only: tap spacing along W if different from `dilation`
 
     def out_hw(self, hh, ww):
         if self.transposed:
@@ -146,7 +147,7 @@ def conv2d(x, layer, res1=None, res2=None, scale=None, shift=None, act=None, pos
     oh, ow = layer.out_hw(hh, ww)
     y = torch.empty((n, oh, ow, layer.cout), dtype=torch.float32, device=x.device)
     d = ConvDesc(n, hh, ww, cin, layer.cout, layer.kh, layer.kw, layer.stride, layer.dilation,
-                 int(layer.transposed), layer.act if act is None else act, layer.post if post is None else post)
+                 int(layer.transposed), layer.act if act is None else act, layer.post if post is None else post, 0)
     sc = layer.scale if scale is None else scale
     sh = layer.shift if shift is None else shift
     if res1 is not None:
@@ -208,7 +209,7 @@ class ConvTC(object):
 Conv3x3TC = ConvTC
 
 
-def conv_tc(x, tcl, res1=None, res2=None, terms=3, out_f32=False, post=None):
+def conv_tc(x, tcl, res1=None, res2=None, terms=3, out_f32=False, post=None, prof=None):
     """x: (hi, lo) split-fp16 NHWC pair.  Returns a split pair, or an fp32 NHWC tensor if out_f32."""
     h = handle()
     xh, xl = x
@@ -227,12 +228,14 @@ def conv_tc(x, tcl, res1=None, res2=None, terms=3, out_f32=False, post=None):
     r1h, r1l = res1 if res1 is not None else (None, None)
     r2h, r2l = res2 if res2 is not None else (None, None)
     d = ConvDesc(n, hh, ww, c, L.cout, L.kh, L.kw, L.stride, L.dilation, int(L.transposed), tcl.act,
-                 L.post if post is None else post)
+                 L.post if post is None else post, int(L.dilation_x))
     e0 = PROF.begin()
     h.check(h.lib.dsin_conv2d_tc(h.ptr, C.byref(d), terms, _p(_chk(xh, torch.float16)), _p(xl), _p(tcl.w_hi),
                                  _p(tcl.w_lo), _p(tcl.scale), _p(tcl.shift), _p(r1h), _p(r1l), _p(r2h), _p(r2l),
                                  _p(yh), _p(yl), _p(yf), _stream()))
-    if e0 is not None:
+    if e0 is not None and prof is not None:
+        PROF.end(e0, prof[0] % terms, prof[1])  # caller-supplied name / algorithmic FLOPs
+    elif e0 is not None:
         pix = n * (hh * ww if L.transposed else oh * ow)
         PROF.end(e0, "tc%d_conv%dx%d_%dto%d%s%s" % (terms, L.kh, L.kw, c, L.cout,
                                                      "_T" if L.transposed else ("_s%d" % L.stride),

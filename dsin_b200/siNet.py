@@ -16,6 +16,7 @@ from . import ops, synth
 
 # "tc3": tcgen05 split-fp16 (fp32-class); "tc1": tcgen05 fp16; "simt": CUDA-core fp32
 MODE = os.environ.get("DSIN_SINET_MODE", "tc3")
+PAIR = os.environ.get("DSIN_SINET_PAIR", "1") != "0"  # pixel-pair form for the even-dilation layers
 
 
 class SiNet(object):
@@ -44,6 +45,25 @@ class SiNet(object):
         self._first_padded = ops.ConvLayer(w1, None, W[S + "g_conv1/biases"], dilation=1, act=ops.ACT_LRELU02,
                                            device=self.device)
         self._tc_first = None
+        # even dilations: "pixel pair" form.  The NHWC tensor (n,H,W,32) is viewed as (n,H,W/2,64); a tap at
+        # x offset +-d becomes +-d/2 pairs, and the 32x32 weight slab becomes a block-diagonal 64x64 one
+        # (pixel parity is preserved by an even shift).  Twice the MMA work (on zeros) but half the TMA rows,
+        # which is what bounds these layers.
+        self._pair = {}
+        for i, rate in enumerate(self.RATES):
+            if i == 0 or rate % 2:
+                continue
+            sc = S + "g_conv%d" % (i + 1)
+            w = np.asarray(W[sc + "/weights"], np.float32)
+            wp = np.zeros((3, 3, 64, 64), dtype=np.float32)
+            wp[:, :, :32, :32] = w
+            wp[:, :, 32:, 32:] = w
+            b = np.asarray(W[sc + "/biases"], np.float32)
+            layer = ops.ConvLayer(wp, None, np.concatenate([b, b]), dilation=rate, act=ops.ACT_LRELU02,
+                                  device=self.device)
+            layer.dilation_x = rate // 2
+            self._pair[i] = layer
+        self._pair_tc = {}
 
     def _run(self, net, post):
         n, hh, ww, _ = net.shape
@@ -73,8 +93,16 @@ class SiNet(object):
                 self._tc_first = ops.ConvTC(self._first_padded)
             cur = ops.concat_normalize_split32(x_dec_nhwc, y_syn_nhwc)
             cur = ops.conv_tc(cur, self._tc_first, terms=terms)
-            for tcl in self._tc[:-1]:
-                cur = ops.conv_tc(cur, tcl, terms=terms)
+            for li, tcl in enumerate(self._tc[:-1], start=1):
+                if PAIR and li in self._pair and ww % 2 == 0 and ww // 2 >= 16:
+                    if li not in self._pair_tc:
+                        self._pair_tc[li] = ops.ConvTC(self._pair[li])
+                    v = (cur[0].view(n, hh, ww // 2, 64), cur[1].view(n, hh, ww // 2, 64))
+                    o = ops.conv_tc(v, self._pair_tc[li], terms=terms,
+                                    prof=("tc%d_conv3x3_32to32_pair_d", 2.0 * n * hh * ww * 9 * 32 * 32))
+                    cur = (o[0].view(n, hh, ww, 32), o[1].view(n, hh, ww, 32))
+                else:
+                    cur = ops.conv_tc(cur, tcl, terms=terms)
             out_nhwc = ops.conv_tc(cur, self._tc[-1], terms=terms, out_f32=True, post=ops.POST_DENORM)
             out = ops.nhwc_to_nchw(out_nhwc)
             out._dsin_nhwc = out_nhwc

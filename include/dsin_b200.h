@@ -66,6 +66,8 @@ int dsin_concat_normalize_split32(dsin_handle_t h, const float* xdec_nhwc, const
  * res1/res2 may be NULL.  post: DSIN_POST_* (denormalise [+clip 0..255], cout must be 3). */
 typedef struct {
   int n, h, w, cin, cout, kh, kw, stride, dilation, transposed, act, post;
+  int dilation_x; /* 0 = same as `dilation`; otherwise the tap spacing along W (tensor-core path only:
+                     used when two pixels are viewed as one 2*C-channel "pair pixel") */
 } dsin_conv_desc_t;
 int dsin_conv2d(dsin_handle_t h, const dsin_conv_desc_t* d, const float* x, const float* w,
                 const float* scale, const float* shift, const float* res1, const float* res2,

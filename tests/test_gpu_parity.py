@@ -482,3 +482,25 @@ def test_cabi_error_codes_and_messages():
     assert h.launch_count() == before
     with pytest.raises(RuntimeError):
         h.check(rc)
+
+
+def test_sinet_pixel_pair_form_equals_plain_form():
+    """Even-dilation SI-Net layers in the pixel-pair form (W/2 x 64 'channels', block-diagonal weights) vs the
+    plain 32-channel tensor-core form, and both vs the oracle."""
+    from dsin_b200 import siNet as sn
+    Wt = calibrated_weights(0)
+    ae = make_ae(120, 288, Wt)
+    rng = np.random.default_rng(3)
+    xd = np.clip(rng.normal(120, 50, (2, 3, 120, 288)), 0, 255).astype(np.float32)
+    ys = np.clip(rng.normal(110, 60, (2, 3, 120, 288)), 0, 255).astype(np.float32)
+    ref = O.denormalize(O.si_net(torch.cat([O.normalize(torch.tensor(xd)), O.normalize(torch.tensor(ys))], 1), Wt))
+    outs = {}
+    old = sn.PAIR
+    try:
+        for pair in (True, False):
+            sn.PAIR = pair
+            outs[pair] = ae._siNet.fused(_nhwc(_dev(xd)), _nhwc(_dev(ys))).cpu()
+    finally:
+        sn.PAIR = old
+    assert float((outs[True] - outs[False]).abs().max()) < 2e-3
+    assert float((outs[True] - ref).abs().max()) < 2e-2
