@@ -51,19 +51,29 @@ class SiNet(object):
         # which is what bounds these layers.
         self._pair = {}
         for i, rate in enumerate(self.RATES):
-            if i == 0 or rate % 2:
-                continue
             sc = S + "g_conv%d" % (i + 1)
-            w = np.asarray(W[sc + "/weights"], np.float32)
-            wp = np.zeros((3, 3, 64, 64), dtype=np.float32)
-            wp[:, :, :32, :32] = w
-            wp[:, :, 32:, 32:] = w
+            w = w1 if i == 0 else np.asarray(W[sc + "/weights"], np.float32)  # layer 0: cin padded to 32
             b = np.asarray(W[sc + "/biases"], np.float32)
-            layer = ops.ConvLayer(wp, None, np.concatenate([b, b]), dilation=rate, act=ops.ACT_LRELU02,
-                                  device=self.device)
-            layer.dilation_x = rate // 2
-            self._pair[i] = layer
+            self._pair[i] = self._pair_layer(w, b, rate)
         self._pair_tc = {}
+
+    def _pair_layer(self, w, b, rate):
+        """3x3 (32->32, dilation `rate`) conv re-expressed on pixel pairs: out parity p at pair j reads input
+        pixel 2j + p + dx, i.e. pair j + floor((p+dx)/2) with parity (p+dx) mod 2.  Even rates keep the parity
+        (block-diagonal weights, pair taps at +-rate/2); odd rates mix parities (pair taps at +-(rate+1)/2 ...)."""
+        offs = sorted({(p_ + (kx - 1) * rate) // 2 for kx in range(3) for p_ in (0, 1)})
+        step = offs[1] - offs[0] if len(offs) > 1 else 1
+        assert len(offs) == 3 and offs[2] - offs[1] == step and offs[1] == 0, offs  # symmetric 3-tap pattern
+        wp = np.zeros((3, 3, 64, 64), dtype=np.float32)
+        for kx in range(3):
+            for p_ in (0, 1):
+                src = p_ + (kx - 1) * rate
+                po, pi = src // 2, src % 2
+                wp[:, offs.index(po), pi * 32:(pi + 1) * 32, p_ * 32:(p_ + 1) * 32] += w[:, kx]
+        layer = ops.ConvLayer(wp, None, np.concatenate([b, b]), dilation=rate, act=ops.ACT_LRELU02,
+                              device=self.device)
+        layer.dilation_x = step
+        return layer
 
     def _run(self, net, post):
         n, hh, ww, _ = net.shape
@@ -92,14 +102,14 @@ class SiNet(object):
             if self._tc_first is None:
                 self._tc_first = ops.ConvTC(self._first_padded)
             cur = ops.concat_normalize_split32(x_dec_nhwc, y_syn_nhwc)
-            cur = ops.conv_tc(cur, self._tc_first, terms=terms)
-            for li, tcl in enumerate(self._tc[:-1], start=1):
-                if PAIR and li in self._pair and ww % 2 == 0 and ww // 2 >= 16:
+            use_pair = PAIR and ww % 2 == 0 and ww // 2 >= 16
+            for li, tcl in enumerate([self._tc_first] + self._tc[:-1]):
+                if use_pair and li in self._pair:
                     if li not in self._pair_tc:
                         self._pair_tc[li] = ops.ConvTC(self._pair[li])
                     v = (cur[0].view(n, hh, ww // 2, 64), cur[1].view(n, hh, ww // 2, 64))
                     o = ops.conv_tc(v, self._pair_tc[li], terms=terms,
-                                    prof=("tc%d_conv3x3_32to32_pair_d", 2.0 * n * hh * ww * 9 * 32 * 32))
+                                    prof=("tc%d_conv3x3_32to32_pair", 2.0 * n * hh * ww * 9 * (6 if li == 0 else 32) * 32))
                     cur = (o[0].view(n, hh, ww, 32), o[1].view(n, hh, ww, 32))
                 else:
                     cur = ops.conv_tc(cur, tcl, terms=terms)
