@@ -247,12 +247,21 @@ def run_ours(args, rank, world, local_rank):
     h2d = 2 * B * 3 * H * W * 1  # uint8 images
     d2h = 4 * B * 3 * H * W * 4 + 8 * B
 
+    # ---------------- quality metrics of the last batch (outside the timed regions) ----------------
+    last = ae.last
+    xs_nhwc = ops.nchw_to_nhwc(dev_sets[(args.steps - 1) % NSETS][0])
+    rec_nhwc = last["x_with_si"]._dsin_nhwc.clamp(0, 255) if hasattr(last.get("x_with_si"), "_dsin_nhwc") else None
+    msssim_sum, msssim_n = 0.0, 0
+    if rec_nhwc is not None:
+        msv = ops.msssim(xs_nhwc, rec_nhwc.contiguous(), form="standard")  # device fp64 MS-SSIM, per image
+        msssim_sum, msssim_n = float(np.sum(msv)), int(msv.shape[0])
+
     # ---------------- reductions over ranks ----------------
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     from dsin_b200.dist import gather_metrics
-    gm = gather_metrics(bits_total, float(npix_total), 0.0, B * args.steps, device=dev)  # the only collective
+    gm = gather_metrics(bits_total, float(npix_total), msssim_sum, msssim_n, device=dev)  # the only collective
     ms_max, e2e_ms_max = float(t[0]), float(t[1])
     if world > 1:
         dist.barrier()
@@ -311,9 +320,61 @@ def run_ours(args, rank, world, local_rank):
         "whole_path_frac_of_bf16_sustained": whole / pk["tf_sust"],
         "kernels": kern,
         "cpu_baseline": cpu,
-        "bpp_aggregate": gm["bpp"], "pairs_processed": gm["n_images"],
+        "bpp_aggregate": gm["bpp"], "msssim_mean_last_batch": gm["msssim"], "pairs_processed": pairs,
+        "quality_note": "random-init weights: bpp / MS-SSIM are plumbing checks here, parity is in tests/",
     }
     print(json.dumps(line), flush=True)
+
+
+def run_sif_only(args, rank, world, local_rank):
+    """BASELINE configs[2]: SI-Finder (prepare + match + gather) in isolation on device-resident inputs."""
+    import torch
+    import __graft_entry__ as g
+    torch.cuda.set_device(local_rank)
+    g.build()
+    from dsin_b200 import ops, synth
+    from dsin_b200.siFinder import match_images
+    pk = peaks()
+    B = args.batch
+    dev = torch.device("cuda", local_rank)
+    x, y = synth.make_batch(min(B, 4), H, W, seed=77)
+    reps = (B + x.shape[0] - 1) // x.shape[0]
+    xd = torch.tensor(np.concatenate([x] * reps)[:B]).to(dev).permute(0, 2, 3, 1).contiguous()
+    yd = torch.tensor(np.concatenate([y] * reps)[:B]).to(dev).permute(0, 2, 3, 1).contiguous()
+    for _ in range(args.warmup):
+        match_images(xd, yd, yd, PH, PW, True)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ops.launch_count()
+    ops.PROF.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        match_images(xd, yd, yd, PH, PW, True)
+    e1.record()
+    torch.cuda.synchronize()
+    ops.PROF.stop()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    prof = ops.PROF.summary()
+    flops = 2.0 * (H - PH + 1) * (W - PW + 1) * (H // PH) * (W // PW) * (PH * PW * 3) * B * args.steps
+    ach = flops / (ms * 1e-3) / 1e12
+    mm = prof.get("sif_match", {"ms": ms})
+    ach_match = flops / (mm["ms"] * 1e-3) / 1e12
+    if rank != 0:
+        return
+    print(json.dumps({
+        "metric": METRIC + " -- SI-Finder only", "value": B * args.steps * H * W * 1e-6 / (ms * 1e-3),
+        "unit": "Mpixels/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 coarse + f32/f64 exact rescoring",
+        "data": "synthetic", "config": {"workload": "BASELINE configs[2]: SI-Finder prepare+match+gather in isolation, "
+                                                    "batch %d of 320x1224" % B, "batch_per_gpu": B},
+        "gpu_launches": int(ops.launch_count() - l0), "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "sif_match", "achieved": ach_match, "peak": pk["tf_sust"],
+                     "unit": "TFLOP/s", "frac": ach_match / pk["tf_sust"], "traffic": None,
+                     "peak_source": pk["src"] + " bf16 dense sustained", "whole_workload_tflops": ach},
+    }), flush=True)
 
 
 def ae_dtype():
@@ -329,6 +390,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="full", choices=["full", "sif"],
+                    help="full = BASELINE configs[1]; sif = configs[2] (SI-Finder in isolation, use --batch 32)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -338,6 +401,9 @@ def main():
         run_reference(args, rank)
         return
     args.warmup = max(args.warmup, 3)
+    if args.workload == "sif":
+        run_sif_only(args, rank, world, local_rank)
+        return
     run_ours(args, rank, world, local_rank)
 
 
