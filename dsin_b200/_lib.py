@@ -52,7 +52,7 @@ SIGNATURES = {
     "dsin_probclass_workspace_bytes": (_I64, [_I, _I, _I, _I, _I]),
     "dsin_probclass_bits": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, C.c_float] + [_P] * 8 + [_P, _P, _P, _P]),
     "dsin_probclass_tc_workspace_bytes": (_I64, [_I, _I, _I, _I]),
-    "dsin_probclass_bits_tc": (_I, [_P, _P, _P, _I, _I, _I, _I, C.c_float] + [_P] * 12 + [_I, _P, _P, _P, _P]),
+    "dsin_probclass_bits_tc": (_I, [_P, _P, _P, _I, _I, _I, _I, C.c_float] + [_P] * 14 + [_I, _P, _P, _P, _P]),
     "dsin_sif_prepare": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "dsin_sif_workspace_bytes": (_I64, [_I, _I, _I, _I, _I, _I]),
     "dsin_sif_match": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),

@@ -44,7 +44,7 @@ struct GP {
   int dout, din;
   // optional fp32 residual with its own geometry (cropped skip of the probability model)
   const float* r1f;
-  int r1_d, r1_oh, r1_ow, r1_dz, r1_dy, r1_dx;
+  int r1_d, r1_oh, r1_ow, r1_dz, r1_dy, r1_dx, r1_c;
 };
 
 constexpr int up1024(int v) { return (v + 1023) / 1024 * 1024; }
@@ -265,7 +265,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
                                     p.r1_ow + ox + p.r1_dx;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (c0 + j < p.cout) f[j] = __fadd_rn(f[j], __ldg(p.r1f + rpix * p.cout + c0 + j));
+              if (c0 + j < p.r1_c) f[j] = __fadd_rn(f[j], __ldg(p.r1f + rpix * p.r1_c + c0 + j));
           }
           if (p.r1h) add_residual16(f, p.r1h, p.r1l, off);
           if (p.r2h) add_residual16(f, p.r2h, p.r2l, off);
@@ -408,7 +408,7 @@ int conv_tc_valid3d(dsin_handle_t h, const ConvTc3dArgs& a, cudaStream_t st) {
     p.dz[t] = a.tap_d[t]; p.dy[t] = a.tap_h[t]; p.dx[t] = a.tap_w[t]; p.wi[t] = a.tap_wi[t];
   }
   p.r1f = a.r1f; p.r1_d = a.r1_d; p.r1_oh = a.r1_oh; p.r1_ow = a.r1_ow;
-  p.r1_dz = a.r1_dz; p.r1_dy = a.r1_dy; p.r1_dx = a.r1_dx;
+  p.r1_dz = a.r1_dz; p.r1_dy = a.r1_dy; p.r1_dx = a.r1_dx; p.r1_c = a.r1_c ? a.r1_c : a.cout;
   p.tiles_w = (p.GW + BW - 1) / BW; p.tiles_h = (p.GH + BH - 1) / BH;
   p.total_tiles = p.n * p.tiles_w * p.tiles_h;
   if (NPAD == 32) return launch_terms<32, 32>(h, a.terms, xh, xl, wh, wl, p, st);

@@ -13,8 +13,8 @@ struct ConvTc3dArgs {
   const float *scale, *shift;
   uint16_t *y_hi, *y_lo;    // split output (cout % 16 == 0) or
   float* y_f32;             // fp32 output (vols, Do, Ho, Wo, cout)
-  const float* r1f;         // optional fp32 residual volume (vols, r1_d, r1_oh, r1_ow, cout), read at +offsets
-  int r1_d, r1_oh, r1_ow, r1_dz, r1_dy, r1_dx;
+  const float* r1f;         // optional fp32 residual volume (vols, r1_d, r1_oh, r1_ow, r1_c), read at +offsets
+  int r1_d, r1_oh, r1_ow, r1_dz, r1_dy, r1_dx, r1_c;
 };
 
 int conv_tc_valid3d(dsin_handle_t h, const ConvTc3dArgs& a, cudaStream_t st);

@@ -227,6 +227,43 @@ __global__ void pc_pad_split_kernel(const float* __restrict__ x, __half* __restr
   lo[idx] = __float2half_rn(f - __half2float(h));
 }
 
+// cross entropy of 6 ReLU'd logits against the target symbol, in bits, + per-image fp64 sums
+__global__ void pc_cross_entropy_kernel(const float* __restrict__ logits, const int64_t* __restrict__ sym,
+                                        float* __restrict__ bits, double* __restrict__ bits_sum, int64_t per_img,
+                                        int n) {
+  const int img = blockIdx.y;
+  __shared__ double s_red[256];
+  double acc = 0.0;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < per_img; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = (int64_t)img * per_img + v;
+    const float* l = logits + g * 6;
+    float a[6];
+#pragma unroll
+    for (int o = 0; o < 6; ++o) a[o] = l[o];
+    float m = a[0];
+#pragma unroll
+    for (int o = 1; o < 6; ++o) m = fmaxf(m, a[o]);
+    float s = 0.f;
+#pragma unroll
+    for (int o = 0; o < 6; ++o) s = __fadd_rn(s, expf(__fsub_rn(a[o], m)));
+    const float lse = __fadd_rn(m, logf(s));
+    const int sy = (int)sym[g];
+    float picked = 0.f;
+#pragma unroll
+    for (int o = 0; o < 6; ++o) picked = (o == sy) ? a[o] : picked;
+    const float bit = __fmul_rn(__fsub_rn(lse, picked), 1.4426950408889634f);
+    if (bits) bits[g] = bit;
+    acc += (double)bit;
+  }
+  s_red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = blockDim.x / 2; st > 0; st >>= 1) {
+    if ((int)threadIdx.x < st) s_red[threadIdx.x] += s_red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(bits_sum + img, s_red[0]);
+}
+
 static void pc_live_taps(ConvTc3dArgs& a) {
   a.ntaps = 0;
   for (int d = 0; d < 2; ++d)
@@ -244,19 +281,22 @@ extern "C" int64_t dsin_probclass_tc_workspace_bytes(int n, int c, int hh, int w
   int64_t v0 = (int64_t)n * (c + 3) * (hh + 6) * (ww + 6);
   int64_t v1 = (int64_t)n * (c + 2) * (hh + 4) * (ww + 4);
   int64_t v2 = (int64_t)n * (c + 1) * (hh + 2) * (ww + 2);
-  return v0 * 24 * 4 + v0 * 32 * 2 * 2 + v1 * 32 * 2 * 2 + v2 * 24 * 4 + 4096;
+  int64_t v3 = (int64_t)n * c * hh * ww;
+  return v0 * 24 * 4 + v0 * 32 * 2 * 2 + v1 * 32 * 2 * 2 + v2 * 32 * 2 * 2 + v3 * 6 * 4 + 8192;
 }
 
 extern "C" int dsin_probclass_bits_tc(dsin_handle_t h, const float* qbar, const int64_t* symbols, int n, int c,
                                       int hh, int ww, float pad_value, const float* w0, const float* b0,
                                       const uint16_t* w1_hi, const uint16_t* w1_lo, const float* scale1,
                                       const float* shift1, const uint16_t* w2_hi, const uint16_t* w2_lo,
-                                      const float* scale2, const float* shift2, const float* w3, const float* b3,
-                                      int terms, float* bits_nchw, double* bits_sum, void* workspace, void* stream) {
+                                      const float* scale2, const float* shift2, const uint16_t* w3_hi,
+                                      const uint16_t* w3_lo, const float* scale3, const float* shift3, int terms,
+                                      float* bits_nchw, double* bits_sum, void* workspace, void* stream) {
   DSIN_REQUIRE(h, qbar && symbols && bits_sum && workspace, "null pointer");
-  DSIN_REQUIRE(h, w0 && b0 && w1_hi && w1_lo && scale1 && shift1 && w2_hi && w2_lo && scale2 && shift2 && w3 && b3,
+  DSIN_REQUIRE(h, w0 && b0 && w1_hi && w1_lo && scale1 && shift1 && w2_hi && w2_lo && scale2 && shift2 && w3_hi &&
+                      w3_lo && scale3 && shift3,
                "null weights");
-  DSIN_REQUIRE(h, hh + 2 >= 8 && ww + 2 >= 16, "volume smaller than one tile");
+  DSIN_REQUIRE(h, hh >= 8 && ww >= 16, "volume smaller than one tile");
   cudaStream_t st = (cudaStream_t)stream;
   const int k = 24;
   int64_t v0 = (int64_t)n * (c + 3) * (hh + 6) * (ww + 6);
@@ -268,7 +308,9 @@ extern "C" int dsin_probclass_bits_tc(dsin_handle_t h, const float* qbar, const 
   __half* x1l = (__half*)base;                    base += (v0 * 32 * 2 + 255) / 256 * 256;
   __half* y1h = (__half*)base;                    base += (v1 * 32 * 2 + 255) / 256 * 256;
   __half* y1l = (__half*)base;                    base += (v1 * 32 * 2 + 255) / 256 * 256;
-  float* a2 = (float*)base;
+  __half* y2h = (__half*)base;                    base += (v2 * 32 * 2 + 255) / 256 * 256;
+  __half* y2l = (__half*)base;                    base += (v2 * 32 * 2 + 255) / 256 * 256;
+  float* logits = (float*)base;
   if (cudaMemsetAsync(bits_sum, 0, sizeof(double) * n, st) != cudaSuccess)
     return dsin_fail(h, DSIN_ERR_CUDA, "%s: memset failed", __func__);
   PcP p;
@@ -291,18 +333,26 @@ extern "C" int dsin_probclass_bits_tc(dsin_handle_t h, const float* qbar, const 
   a.scale = scale1; a.shift = shift1; a.y_hi = (uint16_t*)y1h; a.y_lo = (uint16_t*)y1l;
   int rc = conv_tc_valid3d(h, a, st);
   if (rc != DSIN_OK) return rc;
-  // res1/conv2 (tcgen05): no activation, + skip a0[2:, 2:-2, 2:-2], fp32 24-channel output
-  a.D = c + 2; a.H = hh + 4; a.W = ww + 4; a.cout = 24; a.act = DSIN_ACT_NONE;
+  // res1/conv2 (tcgen05): no activation, + skip a0[2:, 2:-2, 2:-2] (fp32, 24 ch), 32-channel split output
+  a.D = c + 2; a.H = hh + 4; a.W = ww + 4; a.cout = 32; a.act = DSIN_ACT_NONE;
   a.x_hi = (const uint16_t*)y1h; a.x_lo = (const uint16_t*)y1l; a.w_hi = w2_hi; a.w_lo = w2_lo;
-  a.scale = scale2; a.shift = shift2; a.y_hi = nullptr; a.y_lo = nullptr; a.y_f32 = a2;
-  a.r1f = a0; a.r1_d = c + 3; a.r1_oh = hh + 6; a.r1_ow = ww + 6; a.r1_dz = 2; a.r1_dy = 2; a.r1_dx = 2;
+  a.scale = scale2; a.shift = shift2; a.y_hi = (uint16_t*)y2h; a.y_lo = (uint16_t*)y2l; a.y_f32 = nullptr;
+  a.r1f = a0; a.r1_d = c + 3; a.r1_oh = hh + 6; a.r1_ow = ww + 6; a.r1_dz = 2; a.r1_dy = 2; a.r1_dx = 2; a.r1_c = 24;
   rc = conv_tc_valid3d(h, a, st);
   if (rc != DSIN_OK) return rc;
-  // conv2: 24 -> 6, ReLU, fused cross entropy (CUDA cores)
-  p.in = a2; p.w = w3; p.b = b3; p.out = nullptr; p.skip = nullptr; p.Di = c + 1; p.Hi = hh + 2; p.Wi = ww + 2;
-  p.live_mask = pc_live_mask(false); p.relu = 1; p.sym = symbols; p.bits = bits_nchw; p.bits_sum = bits_sum;
-  int64_t v3 = (int64_t)n * c * hh * ww;
-  pc_conv3d_kernel<24, 6, false, true><<<(unsigned)((v3 + 127) / 128), 128, (18 * 24 * 6 + 6) * sizeof(float), st>>>(p);
-  DSIN_LAUNCHED(h);
+  // conv2 (tcgen05): 24 -> 6, ReLU, fp32 logits; then the cross entropy kernel
+  a.D = c + 1; a.H = hh + 2; a.W = ww + 2; a.cout = 6; a.act = DSIN_ACT_RELU;
+  a.x_hi = (const uint16_t*)y2h; a.x_lo = (const uint16_t*)y2l; a.w_hi = w3_hi; a.w_lo = w3_lo;
+  a.scale = scale3; a.shift = shift3; a.y_hi = nullptr; a.y_lo = nullptr; a.y_f32 = logits;
+  a.r1f = nullptr; a.r1_c = 0;
+  rc = conv_tc_valid3d(h, a, st);
+  if (rc != DSIN_OK) return rc;
+  {
+    const int64_t per_img = (int64_t)c * hh * ww;
+    int blocks = (int)((per_img + 255) / 256);
+    if (blocks > 256) blocks = 256;
+    pc_cross_entropy_kernel<<<dim3(blocks, n), 256, 0, st>>>(logits, symbols, bits_nchw, bits_sum, per_img, n);
+    DSIN_LAUNCHED(h);
+  }
   return DSIN_OK;
 }

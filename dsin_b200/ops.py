@@ -293,10 +293,11 @@ class ProbclassTC(object):
         self.w0, self.b0, self.w3, self.b3 = w0, b0, w3, b3
 
         def pack(w, b, cout_pad):
+            cout = w.shape[-1]
             wp = torch.zeros((18, 32, cout_pad), dtype=torch.float32, device=dev)
-            wp[:, :24, :24] = w.reshape(18, 24, 24)
+            wp[:, :24, :cout] = w.reshape(18, 24, cout)
             bp = torch.zeros((cout_pad,), dtype=torch.float32, device=dev)
-            bp[:24] = b
+            bp[:cout] = b
             npad = int(h.lib.dsin_conv_tc_npad(cout_pad))
             hi = torch.empty((18, npad, 32), dtype=torch.float16, device=dev)
             lo = torch.empty((18, npad, 32), dtype=torch.float16, device=dev)
@@ -305,7 +306,8 @@ class ProbclassTC(object):
             return hi, lo, (1.0 / ws).contiguous(), bp
 
         self.l1 = pack(w1, b1, 32)
-        self.l2 = pack(w2, b2, 24)
+        self.l2 = pack(w2, b2, 32)
+        self.l3 = pack(w3, b3, 6)
 
 
 def probclass_bits_tc(qbar_nchw, symbols, pctc, pad_value, terms=3, want_bits=True):
@@ -320,7 +322,8 @@ def probclass_bits_tc(qbar_nchw, symbols, pctc, pad_value, terms=3, want_bits=Tr
     h.check(h.lib.dsin_probclass_bits_tc(
         h.ptr, _p(_chk(qbar_nchw)), _p(_chk(symbols, torch.int64)), n, c, hh, ww, C.c_float(float(pad_value)),
         _p(pctc.w0), _p(pctc.b0), _p(pctc.l1[0]), _p(pctc.l1[1]), _p(pctc.l1[2]), _p(pctc.l1[3]),
-        _p(pctc.l2[0]), _p(pctc.l2[1]), _p(pctc.l2[2]), _p(pctc.l2[3]), _p(pctc.w3), _p(pctc.b3), terms,
+        _p(pctc.l2[0]), _p(pctc.l2[1]), _p(pctc.l2[2]), _p(pctc.l2[3]),
+        _p(pctc.l3[0]), _p(pctc.l3[1]), _p(pctc.l3[2]), _p(pctc.l3[3]), terms,
         _p(bits), _p(sums), _p(work), _stream()))
     if e0 is not None:
         vox = lambda a, b_, c_: float(n * (c + a) * (hh + b_) * (ww + c_))  # noqa: E731

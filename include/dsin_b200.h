@@ -134,16 +134,18 @@ int dsin_probclass_bits(dsin_handle_t h, const float* qbar_nchw, const int64_t* 
                         const float* b2, const float* w3, const float* b3, float* bits_nchw,
                         double* bits_sum, void* workspace, void* stream);
 
-/* Tensor-core variant: the two 24->24 layers run on tcgen05 (weights packed by dsin_pack_conv_w_tc
- * from [18][32][32] / [18][32][24] zero-padded fp32 tensors, scale = 1/wscale, shift = bias); the 1->24
- * stem (w0,b0) and the 24->6 layer with the fused cross entropy (w3,b3) stay on CUDA cores. */
+/* Tensor-core variant: the two 24->24 layers and the 24->6 head run on tcgen05 (weights packed by
+ * dsin_pack_conv_w_tc from [18][32][32] / [18][32][32] / [18][32][6] zero-padded fp32 tensors, scale =
+ * 1/wscale, shift = bias); the 1->24 stem (w0,b0) stays on CUDA cores; a small kernel turns the ReLU'd
+ * logits into bits (log-sum-exp cross entropy * log2 e) and per-image fp64 sums. */
 int64_t dsin_probclass_tc_workspace_bytes(int n, int c, int hh, int ww);
 int dsin_probclass_bits_tc(dsin_handle_t h, const float* qbar_nchw, const int64_t* symbols, int n, int c,
                            int hh, int ww, float pad_value, const float* w0, const float* b0,
                            const uint16_t* w1_hi, const uint16_t* w1_lo, const float* scale1,
                            const float* shift1, const uint16_t* w2_hi, const uint16_t* w2_lo,
-                           const float* scale2, const float* shift2, const float* w3, const float* b3,
-                           int terms, float* bits_nchw, double* bits_sum, void* workspace, void* stream);
+                           const float* scale2, const float* shift2, const uint16_t* w3_hi,
+                           const uint16_t* w3_lo, const float* scale3, const float* shift3, int terms,
+                           float* bits_nchw, double* bits_sum, void* workspace, void* stream);
 
 /* ---- K5-K7: SI-Finder ---------------------------------------------------------------------
  * Replaces SI_full_img (src/siFull_img.py:5-68), siFinder (src/siFinder.py:7-53),
