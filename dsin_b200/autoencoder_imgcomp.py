@@ -26,6 +26,7 @@ arch_param_n = 128
 #   "tc1"  tcgen05, fp16 operands, 1 MMA (fast mode; symbols no longer bit-exact)
 #   "simt" CUDA-core fp32 (v1 kernel, kept as the on-GPU cross-check)
 TRUNK_MODE = os.environ.get("DSIN_TRUNK_MODE", "tc3")
+H13_D2S = os.environ.get("DSIN_H13_D2S", "1") != "0"  # h13 as one 3x3 conv + depth-to-space (else 4 phases)
 COMPUTE_DTYPE = "f16x2-split tensor-core (fp32 accumulate) + f32 CUDA-core"
 
 
@@ -71,6 +72,26 @@ class _Network(object):
                                            act=ops.ACT_RELU if relu else ops.ACT_NONE, post=post,
                                            device=self.device)
 
+    def _transposed_as_conv3x3(self, layer):
+        """A k=5 stride-2 TF-SAME transposed conv (cout = 3) as ONE 3x3 stride-1 conv to 12 phase-channels
+        (2x2 sub-pixel phases x 3 colours) + depth-to-space: out[2a+py, 2b+px] reads in[a+dy, b+dx] with
+        ky = py + 1 - 2dy, kx = px + 1 - 2dx, so every phase only touches the 3x3 neighbourhood of (a, b).
+        The four-phase form fetches the activation tile 25 times, this one 9 times."""
+        w = layer.w.cpu().numpy()  # [5,5,cin,3]
+        k, cin, cout = w.shape[0], w.shape[2], w.shape[3]
+        assert k == 5 and cout == 3
+        w9 = np.zeros((3, 3, cin, 12), dtype=np.float32)
+        for py in range(2):
+            for px in range(2):
+                for dy in (-1, 0, 1):
+                    for dx in (-1, 0, 1):
+                        ky, kx = py + 1 - 2 * dy, px + 1 - 2 * dx
+                        if 0 <= ky < k and 0 <= kx < k:
+                            w9[dy + 1, dx + 1, :, (py * 2 + px) * 3:(py * 2 + px) * 3 + 3] = w[ky, kx]
+        scale = np.tile(layer.scale.cpu().numpy(), 4)
+        shift = np.tile(layer.shift.cpu().numpy(), 4)
+        return ops.ConvLayer(w9, scale, shift, act=layer.act, post=ops.POST_DENORM_CLIP_D2S, device=self.device)
+
     def load_weights(self, W):
         raise NotImplementedError()
 
@@ -94,6 +115,7 @@ class _CVPR(_Network):
         B = self.config.arch_param_B
         E, D = synth.ENC, synth.DEC
         self._tc_layers = {}
+        self._h13_tc = None
         self._centers = torch.from_numpy(np.ascontiguousarray(W[E + "centers"], np.float32)).to(self.device)
         self.centers_host = np.asarray(W[E + "centers"], np.float32).copy()
         self._conv(W, E + "h1", stride=2)
@@ -102,6 +124,7 @@ class _CVPR(_Network):
         self._conv(W, D + "from_bn", stride=2, transposed=True)
         self._conv(W, D + "h12", stride=2, transposed=True)
         self._conv(W, D + "h13", stride=2, transposed=True, relu=False, post=ops.POST_DENORM_CLIP)
+        self._h13_d2s = self._transposed_as_conv3x3(self.layers[D + "h13"])
         for pre, blk, fin in ((E, "res_block_enc_%d/enc_%d_%d", "res_block_enc_final"),
                               (D, "res_block_dec_%d/dec_%d_%d", "dec_after_res")):
             for b in range(B):
@@ -155,6 +178,12 @@ class _CVPR(_Network):
         cur = ops.conv_tc(cur, self._tc(D + "from_bn"), terms=terms)
         cur = self._trunk_tc(cur, D, "res_block_dec_%d/dec_%d_%d", "dec_after_res")
         cur = ops.conv_tc(cur, self._tc(D + "h12"), terms=terms)
+        if H13_D2S:
+            if self._h13_tc is None:
+                self._h13_tc = ops.ConvTC(self._h13_d2s)
+            return ops.conv_tc(cur, self._h13_tc, terms=terms, out_f32=True,  # BN, denormalise, clip, depth-to-space
+                               prof=("tc%d_conv5x5_64to3_T_as3x3", 2.0 * cur[0].shape[0] * cur[0].shape[1]
+                                     * cur[0].shape[2] * 25 * 64 * 3))
         return ops.conv_tc(cur, self._tc(D + "h13"), terms=terms, out_f32=True)  # BN, denormalise, clip fused
 
     # -- CUDA-core fp32 path (v1 kernels; on-GPU cross-check and small-image fallback) -------------

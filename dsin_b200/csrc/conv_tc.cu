@@ -269,6 +269,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
           }
           if (p.r1h) add_residual16(f, p.r1h, p.r1l, off);
           if (p.r2h) add_residual16(f, p.r2h, p.r2l, off);
+          if (p.post == DSIN_POST_DENORM_CLIP_D2S) {
+            // 12 phase-channels -> 2x2 output pixels x 3 colours of a (2*OH, 2*OW, 3) image
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+              const int co = j % 3, ph = j / 3;
+              float t = __fadd_rn(__fmul_rn(f[j], dsin_std(co)), dsin_mean(co));
+              t = fminf(fmaxf(t, 0.f), 255.f);
+              const size_t o2 = (((size_t)n * 2 * p.OH + 2 * oy + (ph >> 1)) * 2 * p.OW + 2 * ox + (ph & 1)) * 3 + co;
+              p.yf[o2] = t;
+            }
+          } else {
           if (p.post != DSIN_POST_NONE) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
@@ -298,6 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
               if (p.yl) reinterpret_cast<uint4*>(p.yl + off)[g] = ul;
             }
           }
+          }  // !D2S
         }
       }
       fence_before_sync();
@@ -449,7 +461,9 @@ extern "C" int dsin_conv2d_tc(dsin_handle_t h, const dsin_conv_desc_t* d, int te
   DSIN_REQUIRE(h, d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
   DSIN_REQUIRE(h, !d->transposed || d->stride == 2, "transposed conv is stride 2");
   DSIN_REQUIRE(h, y_f32 || d->cout % 16 == 0, "split-fp16 output needs cout % 16 == 0");
-  DSIN_REQUIRE(h, d->post == DSIN_POST_NONE || d->cout == 3, "denormalisation needs cout == 3");
+  DSIN_REQUIRE(h, d->post == DSIN_POST_NONE || d->cout == 3 ||
+                      (d->post == DSIN_POST_DENORM_CLIP_D2S && d->cout == 12 && y_f32 && !d->transposed && d->stride == 1),
+               "denormalisation needs cout == 3 (or 12 phase-channels with depth-to-space)");
   const int k = d->kh, KC = kc_of(d->cin), NPAD = npad_of(d->cout);
   const int step = (!d->transposed && d->stride == 2) ? 2 : 1;
   DSIN_REQUIRE(h, d->h >= BH * step && d->w >= BW * step, "image smaller than one tile");

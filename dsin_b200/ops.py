@@ -13,6 +13,8 @@ import torch
 from . import _lib
 from ._lib import ACT_LRELU02, ACT_NONE, ACT_RELU, POST_DENORM, POST_DENORM_CLIP, POST_NONE, ConvDesc  # noqa: F401
 
+POST_DENORM_CLIP_D2S = 3
+
 _handles = {}
 
 
@@ -218,7 +220,11 @@ def conv_tc(x, tcl, res1=None, res2=None, terms=3, out_f32=False, post=None, pro
     assert c == L.cin
     oh, ow = L.out_hw(hh, ww)
     dev = xh.device
-    if out_f32:
+    the_post = L.post if post is None else post
+    if out_f32 and the_post == POST_DENORM_CLIP_D2S:  # 12 phase-channels -> (2h, 2w, 3) image
+        yf = torch.empty((n, 2 * oh, 2 * ow, 3), dtype=torch.float32, device=dev)
+        yh = yl = None
+    elif out_f32:
         yf = torch.empty((n, oh, ow, L.cout), dtype=torch.float32, device=dev)
         yh = yl = None
     else:

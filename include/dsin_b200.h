@@ -29,7 +29,10 @@ typedef struct dsin_handle_s* dsin_handle_t;
 
 enum { DSIN_OK = 0, DSIN_ERR_ARG = -1, DSIN_ERR_CUDA = -2, DSIN_ERR_UNSUPPORTED = -3 };
 enum { DSIN_ACT_NONE = 0, DSIN_ACT_RELU = 1, DSIN_ACT_LRELU02 = 2 };
-enum { DSIN_POST_NONE = 0, DSIN_POST_DENORM_CLIP = 1, DSIN_POST_DENORM = 2 };
+enum { DSIN_POST_NONE = 0, DSIN_POST_DENORM_CLIP = 1, DSIN_POST_DENORM = 2,
+       /* tensor-core path only: cout = 12 = (2x2 sub-pixel phases) x 3 colours; denormalise, clip and
+          scatter to a (2h x 2w x 3) fp32 NHWC image (a stride-2 transposed conv written as one conv) */
+       DSIN_POST_DENORM_CLIP_D2S = 3 };
 
 int dsin_version(void);
 int dsin_create(dsin_handle_t* out, int device);
