@@ -40,6 +40,7 @@ SIGNATURES = {
     "dsin_nhwc_to_nchw": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "dsin_concat_normalize": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "dsin_concat_normalize_split32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "dsin_nchw_to_s2d_split32": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "dsin_conv2d": (_I, [_P, C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "dsin_pack_conv3x3_w": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "dsin_conv3x3_c128_tc": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P]),

@@ -26,6 +26,7 @@ arch_param_n = 128
 #   "tc1"  tcgen05, fp16 operands, 1 MMA (fast mode; symbols no longer bit-exact)
 #   "simt" CUDA-core fp32 (v1 kernel, kept as the on-GPU cross-check)
 TRUNK_MODE = os.environ.get("DSIN_TRUNK_MODE", "tc3")
+H1_S2D = os.environ.get("DSIN_H1_S2D", "1") != "0"    # h1 as space-to-depth + 3x3 tensor-core conv
 H13_D2S = os.environ.get("DSIN_H13_D2S", "1") != "0"  # h13 as one 3x3 conv + depth-to-space (else 4 phases)
 COMPUTE_DTYPE = "f16x2-split tensor-core (fp32 accumulate) + f32 CUDA-core"
 
@@ -92,6 +93,24 @@ class _Network(object):
         shift = np.tile(layer.shift.cpu().numpy(), 4)
         return ops.ConvLayer(w9, scale, shift, act=layer.act, post=ops.POST_DENORM_CLIP_D2S, device=self.device)
 
+    def _stem_as_conv3x3(self, layer):
+        """The 5x5 stride-2 TF-SAME stem (cin = 3) as a 3x3 stride-1 conv over the space-to-depth(2) image
+        (12 channels, padded to 32): input pixel (2(a+dy)+sy, 2(b+dx)+sx) = (2a+ky-1, 2b+kx-1), i.e.
+        ky = 2dy+sy+1, kx = 2dx+sx+1."""
+        w = layer.w.cpu().numpy()  # [5,5,3,cout]
+        k, cin, cout = w.shape[0], w.shape[2], w.shape[3]
+        assert k == 5 and cin == 3
+        w9 = np.zeros((3, 3, 32, cout), dtype=np.float32)
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                for sy in range(2):
+                    for sx in range(2):
+                        ky, kx = 2 * dy + sy + 1, 2 * dx + sx + 1
+                        if 0 <= ky < k and 0 <= kx < k:
+                            w9[dy + 1, dx + 1, (sy * 2 + sx) * 3:(sy * 2 + sx) * 3 + 3, :] = w[ky, kx]
+        return ops.ConvLayer(w9, layer.scale.cpu().numpy(), layer.shift.cpu().numpy(), act=layer.act,
+                             device=self.device)
+
     def load_weights(self, W):
         raise NotImplementedError()
 
@@ -125,6 +144,8 @@ class _CVPR(_Network):
         self._conv(W, D + "h12", stride=2, transposed=True)
         self._conv(W, D + "h13", stride=2, transposed=True, relu=False, post=ops.POST_DENORM_CLIP)
         self._h13_d2s = self._transposed_as_conv3x3(self.layers[D + "h13"])
+        self._h1_s2d = self._stem_as_conv3x3(self.layers[E + "h1"])
+        self._h1_tc = None
         for pre, blk, fin in ((E, "res_block_enc_%d/enc_%d_%d", "res_block_enc_final"),
                               (D, "res_block_dec_%d/dec_%d_%d", "dec_after_res")):
             for b in range(B):
@@ -165,9 +186,16 @@ class _CVPR(_Network):
 
     def _encode_tc(self, x):
         L, E, terms = self.layers, synth.ENC, self._terms()
-        net = ops.nchw_to_nhwc(x, normalize=True)
-        net = ops.conv2d(net, L[E + "h1"])  # cin = 3: CUDA cores (0.5 % of the FLOPs)
-        cur = ops.f32_to_split(net)
+        if H1_S2D and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+            if self._h1_tc is None:
+                self._h1_tc = ops.ConvTC(self._h1_s2d)
+            cur = ops.conv_tc(ops.nchw_to_s2d_split32(x), self._h1_tc, terms=terms,
+                              prof=("tc%d_conv5x5_3to64_s2_as3x3", 2.0 * x.shape[0] * (x.shape[2] // 2)
+                                    * (x.shape[3] // 2) * 25 * 3 * 64))
+        else:
+            net = ops.nchw_to_nhwc(x, normalize=True)
+            net = ops.conv2d(net, L[E + "h1"])  # cin = 3 on CUDA cores
+            cur = ops.f32_to_split(net)
         cur = ops.conv_tc(cur, self._tc(E + "h2"), terms=terms)
         cur = self._trunk_tc(cur, E, "res_block_enc_%d/enc_%d_%d", "res_block_enc_final")
         return ops.conv_tc(cur, self._tc(E + "to_bn"), terms=terms, out_f32=True)

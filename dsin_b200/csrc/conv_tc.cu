@@ -500,6 +500,7 @@ extern "C" int dsin_conv2d_tc(dsin_handle_t h, const dsin_conv_desc_t* d, int te
     if (KC == 64 && NPAD == 48) return launch_terms<64, 48>(h, terms, xh, xl, wh, wl, gp, st);
     if (KC == 64 && NPAD == 16) return launch_terms<64, 16>(h, terms, xh, xl, wh, wl, gp, st);
     if (KC == 32 && NPAD == 128) return launch_terms<32, 128>(h, terms, xh, xl, wh, wl, gp, st);
+    if (KC == 32 && NPAD == 64) return launch_terms<32, 64>(h, terms, xh, xl, wh, wl, gp, st);
     if (KC == 32 && NPAD == 32) return launch_terms<32, 32>(h, terms, xh, xl, wh, wl, gp, st);
     if (KC == 32 && NPAD == 16) return launch_terms<32, 16>(h, terms, xh, xl, wh, wl, gp, st);
     return dsin_fail(h, DSIN_ERR_UNSUPPORTED, "%s: no tensor-core instantiation for this (cin, cout)", __func__);

@@ -58,6 +58,37 @@ __global__ void concat_normalize_split32_kernel(const float* __restrict__ a, con
   reinterpret_cast<uint4*>(lo)[idx] = *reinterpret_cast<const uint4*>(l);
 }
 
+// NCHW image -> normalised, space-to-depth(2) NHWC split-fp16 with 32 channels: out[n, a, b, (sy*2+sx)*3 + c] =
+// norm(x[n, c, 2a+sy, 2b+sx]) (channels 12..31 = 0).  Lets the 5x5 stride-2 stem conv run as a 3x3 stride-1
+// tensor-core conv (src/autoencoder_imgcomp.py:136-144,223).
+__global__ void nchw_to_s2d_split32_kernel(const float* __restrict__ x, __half* __restrict__ hi,
+                                           __half* __restrict__ lo, int n, int hh, int ww) {
+  const int h2 = hh / 2, w2 = ww / 2;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (img, a, b, piece) with 4 pieces of 8 ch
+  if (idx >= (int64_t)n * h2 * w2 * 4) return;
+  const int piece = (int)(idx & 3);
+  int64_t t = idx >> 2;
+  const int b = (int)(t % w2);
+  t /= w2;
+  const int a = (int)(t % h2);
+  const int img = (int)(t / h2);
+  __half h[8], l[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int ch = piece * 8 + e;
+    float v = 0.f;
+    if (ch < 12) {
+      const int c = ch % 3, s = ch / 3, sy = s >> 1, sx = s & 1;
+      const float raw = x[(((int64_t)img * 3 + c) * hh + 2 * a + sy) * ww + 2 * b + sx];
+      v = __fdiv_rn(__fsub_rn(raw, dsin_mean(c)), dsin_std(c));
+    }
+    h[e] = __float2half_rn(v);
+    l[e] = __float2half_rn(v - __half2float(h[e]));
+  }
+  reinterpret_cast<uint4*>(hi)[idx] = *reinterpret_cast<const uint4*>(h);
+  reinterpret_cast<uint4*>(lo)[idx] = *reinterpret_cast<const uint4*>(l);
+}
+
 __global__ void f32_to_split_kernel(const float* __restrict__ x, __half* __restrict__ hi,
                                     __half* __restrict__ lo, int64_t count) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,6 +143,16 @@ int dsin_concat_normalize_split32(dsin_handle_t h, const float* a, const float* 
   int64_t tot = (int64_t)n * hh * ww;
   concat_normalize_split32_kernel<<<(unsigned)((tot * 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       a, b, (__half*)hi, (__half*)lo, tot);
+  DSIN_LAUNCHED(h);
+  return DSIN_OK;
+}
+
+int dsin_nchw_to_s2d_split32(dsin_handle_t h, const float* x_nchw, uint16_t* hi, uint16_t* lo, int n, int hh, int ww,
+                             void* stream) {
+  DSIN_REQUIRE(h, x_nchw && hi && lo && n > 0 && hh % 2 == 0 && ww % 2 == 0, "bad argument");
+  int64_t tot = (int64_t)n * (hh / 2) * (ww / 2) * 4;
+  nchw_to_s2d_split32_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x_nchw, (__half*)hi, (__half*)lo, n, hh, ww);
   DSIN_LAUNCHED(h);
   return DSIN_OK;
 }

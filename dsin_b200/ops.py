@@ -50,6 +50,17 @@ def concat_normalize_split32(xdec_nhwc, ysyn_nhwc):
     return hi, lo
 
 
+def nchw_to_s2d_split32(x):
+    """(n,3,H,W) fp32 image -> normalised space-to-depth(2) split-fp16 (n,H/2,W/2,32) pair."""
+    h = handle()
+    n, c, hh, ww = x.shape
+    assert c == 3 and hh % 2 == 0 and ww % 2 == 0
+    hi = torch.empty((n, hh // 2, ww // 2, 32), dtype=torch.float16, device=x.device)
+    lo = torch.empty((n, hh // 2, ww // 2, 32), dtype=torch.float16, device=x.device)
+    h.check(h.lib.dsin_nchw_to_s2d_split32(h.ptr, _p(_chk(x)), _p(hi), _p(lo), n, hh, ww, _stream()))
+    return hi, lo
+
+
 class _Profiler(object):
     """Optional per-kernel CUDA-event timing (bench.py's roofline): when enabled every wrapped
     launch is bracketed by events on the launching stream and tagged with its algorithmic FLOPs."""

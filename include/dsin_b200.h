@@ -59,6 +59,12 @@ int dsin_concat_normalize(dsin_handle_t h, const float* xdec_nhwc, const float* 
 int dsin_concat_normalize_split32(dsin_handle_t h, const float* xdec_nhwc, const float* ysyn_nhwc,
                                   uint16_t* hi, uint16_t* lo, int n, int hh, int ww, void* stream);
 
+/* NCHW fp32 image (3 channels) -> normalised, space-to-depth(2), 32-channel split-fp16 NHWC
+ * (n, h/2, w/2, 32): channel (sy*2+sx)*3+c = pixel (2a+sy, 2b+sx), colour c; channels 12..31 zero.  With it the
+ * 5x5 stride-2 stem h1 (src/autoencoder_imgcomp.py:223) is a 3x3 stride-1 conv for the tensor-core kernel. */
+int dsin_nchw_to_s2d_split32(dsin_handle_t h, const float* x_nchw, uint16_t* hi, uint16_t* lo, int n, int hh,
+                             int ww, void* stream);
+
 /* ---- K1/K2/K8: convolution + folded BN / bias + activation + residual adds --------------
  * Replaces slim.conv2d / slim.conv2d_transpose + slim.batch_norm + ReLU + the skip adds
  * (src/autoencoder_imgcomp.py:223-266,275-288) and the siNet convs (src/siNet.py:31-40).
