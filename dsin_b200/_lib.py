@@ -19,7 +19,7 @@ class DsinLibraryError(RuntimeError):
 class ConvDesc(C.Structure):
     _fields_ = [(k, C.c_int) for k in
                 ("n", "h", "w", "cin", "cout", "kh", "kw", "stride", "dilation", "transposed", "act", "post",
-                 "dilation_x")]
+                 "dilation_x", "flags")]
 
 
 ACT_NONE, ACT_RELU, ACT_LRELU02 = 0, 1, 2

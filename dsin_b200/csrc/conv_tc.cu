@@ -49,13 +49,14 @@ struct GP {
 
 constexpr int up1024(int v) { return (v + 1023) / 1024 * 1024; }
 
-template <int KC, int NPAD, int TERMS>
+template <int KC, int NPAD, int TERMS, bool PS = false>
 struct Cfg {
   // k-blocks (tap, channel chunk) per pipeline stage: the 32-channel layers have so little MMA work per
   // k-block (N <= 128, K = 32) that the fixed per-stage cost dominates; they take 3 k-blocks per stage.
   static constexpr int kTps = KC == 32 ? 3 : 1;
   static constexpr int kA = up1024(128 * KC * 2);
-  static constexpr int kB = up1024(NPAD * KC * 2);
+  // PS (pair-shared): B is the [32 cout][32 cin] slab (64-byte rows), used for both pixels of the pair
+  static constexpr int kB = PS ? up1024(32 * 32 * 2) : up1024(NPAD * KC * 2);
   static constexpr int kSub = (TERMS == 3 ? 2 : 1) * (kA + kB);
   static constexpr int kStage = kTps * kSub;
   static constexpr int kStagesRaw = (196 * 1024) / kStage;
@@ -91,12 +92,13 @@ __device__ __forceinline__ void add_residual16(float* f, const __half* rh, const
   }
 }
 
-template <int KC, int NPAD, int TERMS>
+template <int KC, int NPAD, int TERMS, bool PS = false>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
                const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
                const __grid_constant__ GP p) {
-  using C = Cfg<KC, NPAD, TERMS>;
+  using C = Cfg<KC, NPAD, TERMS, PS>;
+  static_assert(!PS || (KC == 64 && NPAD == 64), "pair-shared mode is 2 pixels x 32 channels");
   constexpr int S = C::kStages;
   constexpr int STAGE = C::kStage;
   constexpr int TPS = C::kTps;
@@ -141,7 +143,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
   fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
   const int num_kb = p.ntaps * p.nchunks;
-  constexpr uint32_t kBytes = (TERMS == 3 ? 2u : 1u) * (128u * KC * 2u + (uint32_t)NPAD * KC * 2u);
+  constexpr uint32_t kBytes = (TERMS == 3 ? 2u : 1u) * (128u * KC * 2u + (PS ? 32u * 32u * 2u : (uint32_t)NPAD * KC * 2u));
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (converged warp, one lane issues)
@@ -161,13 +163,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
               const int kb = kb0 + t;
               const int tap = kb / p.nchunks, cc = kb - tap * p.nchunks;
               uint8_t* st = tiles + stage * STAGE + t * C::kSub;
-              const int ax = x0 + p.dx[tap], ay = y0 + p.dy[tap], wrow = p.wi[tap] * NPAD;
+              const int ax = x0 + p.dx[tap], ay = y0 + p.dy[tap], wrow = p.wi[tap] * (PS ? 32 : NPAD);
               const int n_in = p.dout ? (n / p.dout) * p.din + (n % p.dout) + p.dz[tap] : n;
               tma_load_4d(st, &tm_xh, &full[stage], cc * KC, ax, ay, n_in);
-              tma_load_2d(st + OFF_B, &tm_wh, &full[stage], cc * KC, wrow);
+              tma_load_2d(st + OFF_B, &tm_wh, &full[stage], PS ? 0 : cc * KC, wrow);
               if (TERMS == 3) {
                 tma_load_4d(st + OFF_ALO, &tm_xl, &full[stage], cc * KC, ax, ay, n_in);
-                tma_load_2d(st + OFF_BLO, &tm_wl, &full[stage], cc * KC, wrow);
+                tma_load_2d(st + OFF_BLO, &tm_wl, &full[stage], PS ? 0 : cc * KC, wrow);
               }
             }
           }
@@ -203,8 +205,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
               if (t >= nsub) break;
               const uint32_t sa = sa0 + t * C::kSub;
               const uint64_t a_hi = make_smem_desc(sa, 16, C::kSbo, C::kLayout);
-              const uint64_t b_hi = make_smem_desc(sa + OFF_B, 16, C::kSbo, C::kLayout);
               const uint64_t a_lo = make_smem_desc(sa + OFF_ALO, 16, C::kSbo, C::kLayout);
+              if constexpr (PS) {
+                // each pixel of the pair (K elements 0..31 / 32..63 of the 128-byte row) times the same 32x32
+                // slab (64-byte-swizzled) into its own 32 accumulator columns
+                constexpr uint32_t idesc32 = make_idesc_f16(128, 32, 0);
+                const uint64_t b_hi = make_smem_desc(sa + OFF_B, 16, 512, LAYOUT_SW64);
+                const uint64_t b_lo = make_smem_desc(sa + OFF_BLO, 16, 512, LAYOUT_SW64);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) {
+                    const uint32_t dt = d_tmem + hf * 32;
+                    umma_f16(dt, a_hi + 4 * hf + 2 * k, b_hi + 2 * k, idesc32, (kb0 | t | k) ? 1u : 0u);
+                    if (TERMS == 3) {
+                      umma_f16(dt, a_hi + 4 * hf + 2 * k, b_lo + 2 * k, idesc32, 1u);
+                      umma_f16(dt, a_lo + 4 * hf + 2 * k, b_hi + 2 * k, idesc32, 1u);
+                    }
+                  }
+                continue;
+              }
+              const uint64_t b_hi = make_smem_desc(sa + OFF_B, 16, C::kSbo, C::kLayout);
               const uint64_t b_lo = make_smem_desc(sa + OFF_BLO, 16, C::kSbo, C::kLayout);
 #pragma unroll
               for (int k = 0; k < KC / 16; ++k) {  // +32 B per K=16 step inside the swizzled row
@@ -358,19 +379,19 @@ __global__ void pack_w_tc_kernel(const float* __restrict__ w, __half* __restrict
   }
 }
 
-template <int KC, int NPAD, int TERMS>
+template <int KC, int NPAD, int TERMS, bool PS = false>
 int launch_one(dsin_handle_t h, const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh,
                const CUtensorMap& wl, const GP& p, cudaStream_t st) {
-  using C = Cfg<KC, NPAD, TERMS>;
+  using C = Cfg<KC, NPAD, TERMS, PS>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<KC, NPAD, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(conv_tc_kernel<KC, NPAD, TERMS, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              C::kSmem) != cudaSuccess)
       return dsin_fail(h, DSIN_ERR_CUDA, "%s: cannot raise dynamic shared memory", __func__);
     configured = true;
   }
   int grid = p.total_tiles < h->sm_count ? p.total_tiles : h->sm_count;
-  conv_tc_kernel<KC, NPAD, TERMS><<<grid, 192, C::kSmem, st>>>(xh, xl, wh, wl, p);
+  conv_tc_kernel<KC, NPAD, TERMS, PS><<<grid, 192, C::kSmem, st>>>(xh, xl, wh, wl, p);
   DSIN_LAUNCHED(h);
   return DSIN_OK;
 }
@@ -473,14 +494,18 @@ extern "C" int dsin_conv2d_tc(dsin_handle_t h, const dsin_conv_desc_t* d, int te
   const uint64_t xs[3] = {(uint64_t)d->cin * 2, (uint64_t)d->w * d->cin * 2, (uint64_t)d->h * d->w * d->cin * 2};
   const uint32_t xb[4] = {(uint32_t)KC, (uint32_t)(BW * step), (uint32_t)(BH * step), 1};
   const uint32_t xe[4] = {1, (uint32_t)step, (uint32_t)step, 1};
-  const uint64_t wd[2] = {(uint64_t)d->cin, (uint64_t)k * k * NPAD};
-  const uint64_t wsb[1] = {(uint64_t)d->cin * 2};
-  const uint32_t wb[2] = {(uint32_t)KC, (uint32_t)NPAD};
+  const bool pair_shared = (d->flags & DSIN_CONV_PAIR_SHARED) != 0;
+  DSIN_REQUIRE(h, !pair_shared || (d->cin == 64 && d->cout == 64 && !d->transposed && d->stride == 1 && !y_f32),
+               "pair-shared mode needs cin = cout = 64, stride 1, split output");
+  const uint64_t wd[2] = {(uint64_t)(pair_shared ? 32 : d->cin), (uint64_t)k * k * (pair_shared ? 32 : NPAD)};
+  const uint64_t wsb[1] = {(uint64_t)(pair_shared ? 32 : d->cin) * 2};
+  const uint32_t wb[2] = {(uint32_t)(pair_shared ? 32 : KC), (uint32_t)(pair_shared ? 32 : NPAD)};
   const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapSwizzle swb = pair_shared ? CU_TENSOR_MAP_SWIZZLE_64B : sw;
   bool ok = encode_tmap(&xh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x_hi, xd, xs, xb, sw, xe) &&
             encode_tmap(&xl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x_lo ? x_lo : x_hi, xd, xs, xb, sw, xe) &&
-            encode_tmap(&wh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w_hi, wd, wsb, wb, sw) &&
-            encode_tmap(&wl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w_lo ? w_lo : w_hi, wd, wsb, wb, sw);
+            encode_tmap(&wh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w_hi, wd, wsb, wb, swb) &&
+            encode_tmap(&wl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w_lo ? w_lo : w_hi, wd, wsb, wb, swb);
   if (!ok) return dsin_fail(h, DSIN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", __func__);
 
   GP p;
@@ -495,6 +520,9 @@ extern "C" int dsin_conv2d_tc(dsin_handle_t h, const dsin_conv_desc_t* d, int te
   cudaStream_t st = (cudaStream_t)stream;
 
   auto launch = [&](const GP& gp) -> int {
+    if (pair_shared)
+      return terms == 3 ? launch_one<64, 64, 3, true>(h, xh, xl, wh, wl, gp, st)
+                        : launch_one<64, 64, 1, true>(h, xh, xl, wh, wl, gp, st);
     if (KC == 64 && NPAD == 128) return launch_terms<64, 128>(h, terms, xh, xl, wh, wl, gp, st);
     if (KC == 64 && NPAD == 64) return launch_terms<64, 64>(h, terms, xh, xl, wh, wl, gp, st);
     if (KC == 64 && NPAD == 48) return launch_terms<64, 48>(h, terms, xh, xl, wh, wl, gp, st);
@@ -573,7 +601,7 @@ extern "C" int dsin_conv3x3_c128_tc(dsin_handle_t h, int n, int hh, int ww, cons
                                     const float* scale, const float* shift, int act, const uint16_t* res1_hi,
                                     const uint16_t* res1_lo, const uint16_t* res2_hi, const uint16_t* res2_lo,
                                     uint16_t* y_hi, uint16_t* y_lo, int terms, void* stream) {
-  dsin_conv_desc_t d = {n, hh, ww, 128, 128, 3, 3, 1, 1, 0, act, DSIN_POST_NONE, 0};
+  dsin_conv_desc_t d = {n, hh, ww, 128, 128, 3, 3, 1, 1, 0, act, DSIN_POST_NONE, 0, 0};
   DSIN_REQUIRE(h, y_hi && (terms == 1 || y_lo), "null output");
   return dsin_conv2d_tc(h, &d, terms, x_hi, x_lo, w_hi, w_lo, scale, shift, res1_hi, res1_lo, res2_hi, res2_lo, y_hi,
                         y_lo, nullptr, stream);

@@ -145,6 +145,7 @@ class ConvLayer(object):
         self.shift = None if shift is None else torch.from_numpy(np.ascontiguousarray(shift, np.float32)).to(device)
         self.stride, self.dilation, self.transposed, self.act, self.post = stride, dilation, transposed, act, post
         self.dilation_x = 0  # tensor-core path only: tap spacing along W if different from `dilation`
+        self.flags = 0       # DSIN_CONV_* flags (tensor-core path only)
 
     def out_hw(self, hh, ww):
         if self.transposed:
@@ -160,7 +161,7 @@ def conv2d(x, layer, res1=None, res2=None, scale=None, shift=None, act=None, pos
     oh, ow = layer.out_hw(hh, ww)
     y = torch.empty((n, oh, ow, layer.cout), dtype=torch.float32, device=x.device)
     d = ConvDesc(n, hh, ww, cin, layer.cout, layer.kh, layer.kw, layer.stride, layer.dilation,
-                 int(layer.transposed), layer.act if act is None else act, layer.post if post is None else post, 0)
+                 int(layer.transposed), layer.act if act is None else act, layer.post if post is None else post, 0, 0)
     sc = layer.scale if scale is None else scale
     sh = layer.shift if shift is None else shift
     if res1 is not None:
@@ -221,6 +222,34 @@ class ConvTC(object):
 
 Conv3x3TC = ConvTC
 
+CONV_PAIR_SHARED = 1
+
+
+class _PairDesc(object):
+    """Geometry of a pixel-pair conv (cin = cout = 64) whose weights are a shared 32x32 slab."""
+
+    def __init__(self, base, rate):
+        self.kh, self.kw, self.cin, self.cout = base.kh, base.kw, 64, 64
+        self.stride, self.dilation, self.transposed, self.act, self.post = 1, rate, False, base.act, POST_NONE
+        self.dilation_x, self.flags = rate // 2, CONV_PAIR_SHARED
+
+    def out_hw(self, hh, ww):
+        return hh, ww
+
+
+class PairSharedTC(object):
+    """Even-dilation 32->32 conv applied to pixel pairs: reuses the packed [taps][32][32] weights of the plain
+    tensor-core layer; scale/shift are duplicated for the two pixels of a pair."""
+
+    def __init__(self, tcl32, rate):
+        assert rate % 2 == 0 and tcl32.layer.cin == 32 and tcl32.layer.cout == 32
+        self.layer = _PairDesc(tcl32.layer, rate)
+        self.w_hi, self.w_lo = tcl32.w_hi, tcl32.w_lo
+        self.scale = torch.cat([tcl32.scale, tcl32.scale]).contiguous()
+        self.shift = torch.cat([tcl32.shift, tcl32.shift]).contiguous()
+        self.act = tcl32.act
+
+
 
 def conv_tc(x, tcl, res1=None, res2=None, terms=3, out_f32=False, post=None, prof=None):
     """x: (hi, lo) split-fp16 NHWC pair.  Returns a split pair, or an fp32 NHWC tensor if out_f32."""
@@ -245,7 +274,7 @@ def conv_tc(x, tcl, res1=None, res2=None, terms=3, out_f32=False, post=None, pro
     r1h, r1l = res1 if res1 is not None else (None, None)
     r2h, r2l = res2 if res2 is not None else (None, None)
     d = ConvDesc(n, hh, ww, c, L.cout, L.kh, L.kw, L.stride, L.dilation, int(L.transposed), tcl.act,
-                 L.post if post is None else post, int(L.dilation_x))
+                 L.post if post is None else post, int(L.dilation_x), int(getattr(L, "flags", 0)))
     e0 = PROF.begin()
     h.check(h.lib.dsin_conv2d_tc(h.ptr, C.byref(d), terms, _p(_chk(xh, torch.float16)), _p(xl), _p(tcl.w_hi),
                                  _p(tcl.w_lo), _p(tcl.scale), _p(tcl.shift), _p(r1h), _p(r1l), _p(r2h), _p(r2l),

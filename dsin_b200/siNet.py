@@ -16,7 +16,8 @@ from . import ops, synth
 
 # "tc3": tcgen05 split-fp16 (fp32-class); "tc1": tcgen05 fp16; "simt": CUDA-core fp32
 MODE = os.environ.get("DSIN_SINET_MODE", "tc3")
-PAIR = os.environ.get("DSIN_SINET_PAIR", "1") != "0"  # pixel-pair form for the even-dilation layers
+PAIR = os.environ.get("DSIN_SINET_PAIR", "1") != "0"  # pixel-pair form (128-byte TMA rows)
+PAIR_SHARED = os.environ.get("DSIN_SINET_PAIR_SHARED", "1") != "0"  # even dilation: no MMAs on zero blocks
 
 
 class SiNet(object):
@@ -106,7 +107,11 @@ class SiNet(object):
             for li, tcl in enumerate([self._tc_first] + self._tc[:-1]):
                 if use_pair and li in self._pair:
                     if li not in self._pair_tc:
-                        self._pair_tc[li] = ops.ConvTC(self._pair[li])
+                        rate = self.RATES[li]
+                        if PAIR_SHARED and li >= 1 and rate % 2 == 0:  # parity-preserving: shared 32x32 slab
+                            self._pair_tc[li] = ops.PairSharedTC(self._tc[li - 1], rate)
+                        else:
+                            self._pair_tc[li] = ops.ConvTC(self._pair[li])
                     v = (cur[0].view(n, hh, ww // 2, 64), cur[1].view(n, hh, ww // 2, 64))
                     o = ops.conv_tc(v, self._pair_tc[li], terms=terms,
                                     prof=("tc%d_conv3x3_32to32_pair", 2.0 * n * hh * ww * 9 * (6 if li == 0 else 32) * 32))

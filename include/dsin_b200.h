@@ -77,7 +77,10 @@ typedef struct {
   int n, h, w, cin, cout, kh, kw, stride, dilation, transposed, act, post;
   int dilation_x; /* 0 = same as `dilation`; otherwise the tap spacing along W (tensor-core path only:
                      used when two pixels are viewed as one 2*C-channel "pair pixel") */
+  int flags;      /* DSIN_CONV_PAIR_SHARED (tensor-core path, cin = cout = 64 = two pixels x 32 channels, even
+                     dilation): the weights are the plain [taps][32][32] slab, applied to each pixel of the pair */
 } dsin_conv_desc_t;
+enum { DSIN_CONV_PAIR_SHARED = 1 };
 int dsin_conv2d(dsin_handle_t h, const dsin_conv_desc_t* d, const float* x, const float* w,
                 const float* scale, const float* shift, const float* res1, const float* res2,
                 float* y, void* stream);
