@@ -31,6 +31,7 @@ if os.environ.get("DSIN_BENCH_HW"):  # test hook only (tests/test_bench_contract
     H, W = (int(v) for v in os.environ["DSIN_BENCH_HW"].split("x"))
 PH, PW = 20, 24
 GFLOP_PER_PAIR_FULL = 1893.9  # SURVEY App. B / BASELINE.md section 4
+GFLOP_PER_PAIR_DECODE = 1640.0  # decode-side region: AE(y) + decoder(x) + SI-Finder + SI-Net
 METRIC = "Mpixels/s decode (320x1224 pairs)"
 
 
@@ -235,6 +236,19 @@ def run_ours(args, rank, world, local_rank):
         bits_total += float(bs.sum().item())
         npix_total += B * H * W
 
+    # ---------------- decode-side region: receiver only, qbar(x) and y given ----------------
+    qb_sets = [ae.reconstruct_device(*dev_sets[s_])["qbar"].clone() for s_ in range(NSETS)]
+    for i in range(min(2, args.warmup)):
+        ae.decode_side_device(qb_sets[i % NSETS], dev_sets[i % NSETS][1])
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    d0.record()
+    for i in range(args.steps):
+        ae.decode_side_device(qb_sets[i % NSETS], dev_sets[i % NSETS][1])
+    d1.record()
+    sync_all()
+    dec_ms = d0.elapsed_time(d1)
+
     # ---------------- end-to-end timing (public numpy API, pinned host buffers) ----------------
     for i in range(min(2, args.warmup)):
         ae.siNet_get_reconstructed(*host_sets[i % NSETS])
@@ -257,12 +271,12 @@ def run_ours(args, rank, world, local_rank):
         msssim_sum, msssim_n = float(np.sum(msv)), int(msv.shape[0])
 
     # ---------------- reductions over ranks ----------------
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, dec_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     from dsin_b200.dist import gather_metrics
     gm = gather_metrics(bits_total, float(npix_total), msssim_sum, msssim_n, device=dev)  # the only collective
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    ms_max, e2e_ms_max, dec_ms_max = float(t[0]), float(t[1]), float(t[2])
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -316,6 +330,13 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
+        "regions": {
+            "full": {"value": value, "unit": "Mpixels/s", "gflop_per_pair": GFLOP_PER_PAIR_FULL,
+                     "what": "encode(x)+bpp + decode-side (the headline `value`)"},
+            "decode_side": {"value": pairs * H * W * 1e-6 / (dec_ms_max * 1e-3), "unit": "Mpixels/s",
+                            "ms_per_step": dec_ms_max / args.steps, "gflop_per_pair": GFLOP_PER_PAIR_DECODE,
+                            "tflops_per_gpu": pairs / world * GFLOP_PER_PAIR_DECODE / (dec_ms_max * 1e-3) / 1e3,
+                            "what": "receiver only: AE(y)->y_dec, decoder(qbar_x), SI-Finder, SI-Net"}},
         "whole_path_tflops_per_gpu": whole,
         "whole_path_frac_of_bf16_sustained": whole / pk["tf_sust"],
         "kernels": kern,

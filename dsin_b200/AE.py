@@ -151,17 +151,31 @@ class AE(object):
         dec = self._decode(z.qbar, self.ae_imgcomp, is_training=False)
         if on_decoded is not None:
             on_decoded(dec)
-        dec_nhwc = dec._dsin_nhwc
-        y_dec, x_dec = dec[:B], dec[B:]
-        y_dec._dsin_nhwc, x_dec._dsin_nhwc = dec_nhwc[:B], dec_nhwc[B:]
         # bpp of x only (src/AE.py:85-87)
         qx, sx = z.qbar[B:], z.symbols[B:]
         bc = self.pc_imgcomp.bitcost(qx, sx, is_training=False,
                                      pad_value=self.pc_imgcomp.auto_pad_value(self.ae_imgcomp))
-        out = {"y_dec": y_dec, "x_dec": x_dec, "symbols": sx, "bits": bc, "bits_sum": bc._dsin_sum}
+        out = {"symbols": sx, "qbar": qx, "bits": bc, "bits_sum": bc._dsin_sum}
+        out.update(self._side_information(dec, y, B))
+        return out
+
+    def decode_side_device(self, qbar_x, y):
+        """Receiver side only (SURVEY 8d "decode-side" region): the quantised bottleneck of x (what the
+        bitstream carries) and the side image y -> AE(y) (src/AE.py:150-152), decoder(x) (src/AE.py:57),
+        SI-Finder and SI-Net (src/AE.py:60-69).  No encoder pass over x and no probability model."""
+        B = y.shape[0]
+        zy = self._encode(y, self.ae_imgcomp, is_training=False)
+        dec = self._decode(torch.cat([zy.qbar, qbar_x], dim=0), self.ae_imgcomp, is_training=False)
+        return self._side_information(dec, y, B)
+
+    def _side_information(self, dec, y, B):
+        dec_nhwc = dec._dsin_nhwc
+        y_dec, x_dec = dec[:B], dec[B:]
+        y_dec._dsin_nhwc, x_dec._dsin_nhwc = dec_nhwc[:B], dec_nhwc[B:]
+        out = {"y_dec": y_dec, "x_dec": x_dec}
         if self.AE_only:
-            out["y_syn"] = torch.zeros_like(x)
-            out["x_with_si"] = torch.zeros_like(x)
+            out["y_syn"] = torch.zeros_like(y)
+            out["x_with_si"] = torch.zeros_like(y)
             return out
         y_syn, _ncc, _arg, _q, _r, row, col, _xp, _yp = self._SI_full_img(
             x_dec, y, self.mask, self._y_patch_h, self._y_patch_w, self.ae_config, y_dec)
@@ -170,8 +184,8 @@ class AE(object):
             x_with_si = fused(x_dec._dsin_nhwc, y_syn._dsin_nhwc)
         else:  # generic callable: normalise/concat/denormalise with torch elementwise ops
             mean, var = self.get_mean_var()
-            m = torch.from_numpy(mean).to(x.device)
-            s = torch.from_numpy(np.sqrt(var + 1e-10).astype(np.float32)).to(x.device)
+            m = torch.from_numpy(mean).to(y.device)
+            s = torch.from_numpy(np.sqrt(var + 1e-10).astype(np.float32)).to(y.device)
             cat = torch.cat([(x_dec - m) / s, (y_syn - m) / s], dim=1)
             x_with_si = self._siNet(cat) * s + m
         out.update({"y_syn": y_syn, "x_with_si": x_with_si, "row": row, "col": col,

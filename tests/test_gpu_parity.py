@@ -504,3 +504,18 @@ def test_sinet_pixel_pair_form_equals_plain_form():
         sn.PAIR = old
     assert float((outs[True] - outs[False]).abs().max()) < 2e-3
     assert float((outs[True] - ref).abs().max()) < 2e-2
+
+
+def test_decode_side_region_equals_full_path():
+    """The receiver-only region (qbar of x + y -> AE(y), decoder(x), SI-Finder, SI-Net) must give
+    exactly what the full call gives: pairs and images are independent, so splitting the encoder pass
+    changes nothing bit for bit."""
+    ae = make_ae(80, 144, calibrated_weights(0))
+    x, y = synth.make_batch(2, 80, 144, seed=31)
+    xd, yd = _dev(x), _dev(y)
+    full = ae.reconstruct_device(xd, yd)
+    qb = full["qbar"].clone()
+    keep = {k: full[k].clone() for k in ("y_dec", "x_dec", "y_syn", "x_with_si", "row", "col")}
+    part = ae.decode_side_device(qb, yd)
+    for k, v in keep.items():
+        assert torch.equal(v, part[k]), k
