@@ -8,8 +8,8 @@
 Differences (documented in DESIGN.md): inputs may hold B >= 1 pairs (the reference's SI path is
 hard-wired to batch 1, src/AE.py:26) -- each pair is processed with batch-1 semantics and bpp is
 the batch aggregate of bits.bitcost_to_bpp; the two autoencoder passes (on y and on x) run as
-one batch of 2B images; weights live in an .npz keyed by the TF variable names; training entry
-points raise NotImplementedError.
+one batch of 2B images; weights are read from a TF-V2 checkpoint (tf_checkpoint.py, no TensorFlow) or an
+.npz keyed by the TF variable names; training entry points raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -23,6 +23,7 @@ from . import bits_imgcomp as bits
 from . import ops
 from . import probclass_imgcomp as probclass
 from . import synth
+from . import tf_checkpoint
 from .siFinder import GaussianPrior
 
 
@@ -76,18 +77,37 @@ class AE(object):
             self._siNet.load_weights(W)
 
     def save_model(self, save_path):
-        path = save_path if save_path.endswith(".npz") else save_path + ".npz"
-        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-        synth.save_weights(path, self.weights)
+        """src/AE.py:154-156 (`tf.train.Saver.save`): writes a TF-V2 checkpoint `<save_path>.index` +
+        `<save_path>.data-00000-of-00001` keyed by the TF variable names; a path ending in .npz writes the
+        same dictionary as an .npz instead."""
+        if save_path.endswith(".npz"):
+            os.makedirs(os.path.dirname(os.path.abspath(save_path)), exist_ok=True)
+            synth.save_weights(save_path, self.weights)
+        else:
+            tf_checkpoint.write_checkpoint(save_path, self.weights)
+
+    def _restore_names(self):
+        """The variables `load_model` of the reference restores for inference (src/AE.py:158-172): scopes
+        encoder/encoder_body, decoder, imgcomp and -- unless AE_only -- siNetwork.  Optimizer slots and the
+        training step of a training checkpoint are ignored."""
+        names = [k for k in synth.variable_names(self.ae_config.arch_param_B) if
+                 k.startswith(("encoder/encoder_body/", "decoder/", "imgcomp/"))
+                 or (not self.AE_only and k.startswith("siNetwork/"))]
+        return names
 
     def load_model(self, load_path):
-        path = load_path if load_path.endswith(".npz") else load_path + ".npz"
-        if not os.path.exists(path):
-            raise FileNotFoundError(
-                "{} not found.  dsin_b200 reads weights from an .npz keyed by the TF variable names; "
-                "a TF-V2 checkpoint importer is not built yet (SURVEY 8f N1)".format(path))
-        print("Loading " + path)
-        self.set_weights(synth.load_weights(path))
+        """Accepts what `tf.train.Saver.restore` takes (a TF-V2 checkpoint prefix, src/AE.py:158-175) or an
+        .npz keyed by the same variable names."""
+        npz = load_path if load_path.endswith(".npz") else load_path + ".npz"
+        if not load_path.endswith(".npz") and tf_checkpoint.checkpoint_exists(load_path):
+            print("Loading " + load_path)
+            W = tf_checkpoint.read_checkpoint(load_path, names=self._restore_names())
+        elif os.path.exists(npz):
+            print("Loading " + npz)
+            W = synth.load_weights(npz)
+        else:
+            raise FileNotFoundError("neither {}.index (TF-V2 checkpoint) nor {} found".format(load_path, npz))
+        self.set_weights(W)
 
     # ------------------------------------------------------------------ helpers kept from the reference
     def create_gaussian_masks(self):

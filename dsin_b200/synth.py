@@ -101,6 +101,16 @@ def make_weights(seed=0, B=5, num_chan_bn=32, num_centers=6, pc_k=24, residual_g
     return W
 
 
+_NAMES = {}
+
+
+def variable_names(B=5):
+    """TF variable names of the inference graph, in sorted order."""
+    if B not in _NAMES:
+        _NAMES[B] = sorted(make_weights(0, B=B))
+    return list(_NAMES[B])
+
+
 def set_bn_stats(W, scope, mean, var):
     W[scope + "/BatchNorm/moving_mean"] = np.asarray(mean, dtype=np.float32)
     W[scope + "/BatchNorm/moving_variance"] = np.maximum(np.asarray(var, dtype=np.float32), 1e-6)

@@ -2,6 +2,8 @@
 identical seeded inputs/weights.  Integer outputs (symbols, SI-Finder row/col) must be equal
 except at near-ties adjudicated by the float64 oracle; floats within the stated tolerances
 (north_star: |d bpp| <= 1e-5, |d MS-SSIM| <= 1e-4)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -519,3 +521,65 @@ def test_decode_side_region_equals_full_path():
     part = ae.decode_side_device(qb, yd)
     for k, v in keep.items():
         assert torch.equal(v, part[k]), k
+
+
+def test_tf_checkpoint_save_restore_and_main_drop_in(tmp_path, monkeypatch):
+    """SURVEY 8f N1+N2: `save_model` writes a TF-V2 checkpoint, `load_model` restores the scope-filtered
+    variables from it, and the reference's README inference recipe (`python main.py` in a directory holding
+    run_configs/, data_paths/<list>, weights/<name>/model.*) runs end to end: pair lists -> PNG decode ->
+    centre crop -> siNet_get_reconstructed -> PNG named <i>_<bpp>bpp.png (uint8 truncation)."""
+    from PIL import Image
+    from dsin_b200 import main as dmain
+    Wt = calibrated_weights(0)
+    ae = make_ae(80, 144, Wt)
+    prefix = str(tmp_path / "weights" / "tiny_model" / "model")
+    ae.save_model(prefix)
+    assert os.path.isfile(prefix + ".index") and os.path.isfile(prefix + ".data-00000-of-00001")
+    # a fresh AE with different weights, then restore
+    ae2 = make_ae(80, 144, synth.make_weights(3))
+    ae2.load_model(prefix)
+    x, y = synth.make_batch(1, 80, 144, seed=77)
+    ref = ae.siNet_get_reconstructed(x, y)
+    ref = [np.array(a) for a in ref]
+    got = ae2.siNet_get_reconstructed(x, y)
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, np.array(b))
+    with pytest.raises(FileNotFoundError):
+        ae2.load_model(str(tmp_path / "weights" / "missing" / "model"))
+
+    # --- the drop-in directory layout of the reference's README recipe
+    root = str(tmp_path / "kitti") + os.sep
+    os.makedirs(root + "image_2"), os.makedirs(root + "image_3"), os.makedirs(tmp_path / "data_paths")
+    xs, ys = synth.make_batch(2, 96, 160, seed=5)   # larger than the crop: exercises the centre crop
+    lines = []
+    for i in range(2):
+        for cam, arr in (("image_2", xs), ("image_3", ys)):
+            rel = "%s/%06d_10.png" % (cam, i)
+            Image.fromarray(arr[i].transpose(1, 2, 0).astype(np.uint8), "RGB").save(root + rel)
+            lines.append(rel)
+    (tmp_path / "data_paths" / "KITTI_stereo_test.txt").write_text("\n".join(lines) + "\n")
+    cfg_src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dsin_b200", "run_configs")
+    txt = open(os.path.join(cfg_src, "ae_run_configs")).read()
+    txt = txt.replace("crop_size = (320,1224)", "crop_size = (80,144)")
+    txt = txt.replace("root_data = '/root/sharedfolder2/'", "root_data = %r" % root)
+    txt = txt.replace("load_model_name = 'KITTI_stereo_target_bpp0.02'", "load_model_name = 'tiny_model'")
+    assert "tiny_model" in txt and "(80,144)" in txt and root in txt
+    os.makedirs(tmp_path / "run_configs")
+    (tmp_path / "run_configs" / "ae_run_configs").write_text(txt)
+    monkeypatch.chdir(tmp_path)
+    args = dmain.build_parser().parse_args(
+        ["-ae_config", str(tmp_path / "run_configs" / "ae_run_configs"), "--create_loss_list"])
+    bpps = dmain.main(dmain.get_run_params(args), args)
+    assert len(bpps) == 2 and all(b > 0 for b in bpps)
+    # same numbers as the direct call on the centre crops
+    for i in range(2):
+        xc = xs[i:i + 1, :, 8:88, 8:152].astype(np.uint8)
+        yc = ys[i:i + 1, :, 8:88, 8:152].astype(np.uint8)
+        _yd, _ys, _xd, xsi, bpp = ae.siNet_get_reconstructed(xc, yc)
+        assert float(bpp) == bpps[i]
+        png = str(tmp_path / "images" / "tiny_model" / ("%d_%.5fbpp.png" % (i, bpp)))
+        assert os.path.isfile(png), os.listdir(tmp_path / "images" / "tiny_model")
+        assert np.array_equal(np.asarray(Image.open(png)),
+                              np.clip(np.array(xsi[0]), 0, 255).transpose(1, 2, 0).astype("uint8"))
+    for name in ("bpp_list_", "l1_list_", "psnr_list_", "msssim_list_", "mse_list_x_y_syn_", "avg_Pearson_list_x_y_syn_"):
+        assert len(open(str(tmp_path / "images" / (name + "tiny_model.txt"))).read().split()) == 2
