@@ -17,12 +17,14 @@ int dsin_create(dsin_handle_t* out, int device) {
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   h->launches = 0;
+  h->ident128 = nullptr;
   h->err[0] = 0;
   *out = h;
   return DSIN_OK;
 }
 
 int dsin_destroy(dsin_handle_t h) {
+  if (h && h->ident128) cudaFree(h->ident128);
   delete h;
   return DSIN_OK;
 }

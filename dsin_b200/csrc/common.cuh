@@ -11,6 +11,7 @@ struct dsin_handle_s {
   int device;
   int sm_count;
   int64_t launches;
+  void* ident128;  // 128x128 fp16 identity (device), lazily created by the CTA-pair conv (residual adds on the MMA)
   char err[512];
 };
 

@@ -29,5 +29,11 @@ struct ConvTc2Args {
   int tiles_w, tiles_h, total_tiles;
   short dy[25], dx[25], wi[25];
 };
+struct ConvTc2Res {  // TMA maps of the residual planes (r1 hi, r1 lo, r2 hi, r2 lo) and of the identity slab
+  CUtensorMap plane[4];
+  CUtensorMap ident;
+  int nres;        // residual tensors (0..2)
+  int has_lo[2];   // residual i carries a lo plane
+};
 int conv_tc2_launch(dsin_handle_t h, int terms, const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh,
                     const CUtensorMap& wl, const ConvTc2Args& p, cudaStream_t st);

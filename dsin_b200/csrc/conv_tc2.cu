@@ -12,6 +12,15 @@
 // full barrier (cta_group::2 TMA); the leader's MMA warp issues tcgen05.mma.cta_group::2 and commits with
 // multicast to the per-CTA empty / accumulator-full barriers; every epilogue warp of both CTAs arrives on
 // the leader's accumulator-empty barrier.  Accumulators stay in each CTA's own TMEM (double buffered).
+//
+// Residual inputs (the skip adds of src/autoencoder_imgcomp.py:275-288) are added ON THE TENSOR PIPE: each
+// residual plane tile is TMA-loaded as an A operand and multiplied by a 128x128 identity slab into a second
+// accumulator (TMEM columns +128; products with 1.0 are exact, fp32 accumulation), 2 extra pipeline stages
+// per residual tensor.  The epilogue then reads both accumulators from TMEM and never touches global memory
+// for inputs: the previous per-thread 16-byte residual loads at a 256-byte stride kept the tensor pipe only
+// 58 % busy on those layers (profiles/r1_v7_ncu_full_conv_tc2_b8.txt).
+#include <vector>
+
 #include "tc_common.cuh"
 #include "conv_tc.cuh"
 
@@ -25,30 +34,22 @@ constexpr int B_HALF = 64 * 128;   // 64 couts x 64 ch fp16
 
 template <int TERMS>
 struct Cfg2 {
-  static constexpr int kStage = (TERMS == 3 ? 2 : 1) * (A_TILE + B_HALF);
-  static constexpr int kStages = TERMS == 3 ? 4 : 8;
+  // TERMS == 1 stages keep room for the lo plane of a residual tile
+  static constexpr int kStage = TERMS == 3 ? 2 * (A_TILE + B_HALF) : 2 * A_TILE + B_HALF;
+  static constexpr int kStages = TERMS == 3 ? 4 : 5;
   static constexpr int kSmem = kStages * kStage + 1024 + 2048;
 };
-
-__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-  const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = __half22float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
 
 template <int TERMS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
                 const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
-                const __grid_constant__ ConvTc2Args p) {
+                const __grid_constant__ ConvTc2Res rm, const __grid_constant__ ConvTc2Args p) {
   using C = Cfg2<TERMS>;
   constexpr int S = C::kStages;
   constexpr int STAGE = C::kStage;
   constexpr int OFF_B = A_TILE, OFF_ALO = A_TILE + B_HALF, OFF_BLO = 2 * A_TILE + B_HALF;
+  constexpr int OFF_ALO_RES = A_TILE + B_HALF;  // lo plane of a residual (TERMS == 1 stages are padded to hold it)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -85,7 +86,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
     s_scale[i] = p.scale[i];
     s_shift[i] = p.shift[i];
   }
-  if (warp == 1) tmem_alloc2(tmem_ptr, 256);
+  if (warp == 1) tmem_alloc2(tmem_ptr, 512);
   fence_before_sync();
   __syncthreads();
   cluster_sync_all();
@@ -126,6 +127,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
           phase ^= 1u;
         }
       }
+      // residual tensors ride the same pipeline: plane tiles as A operands, an identity slab as B
+      for (int r = 0; r < rm.nres; ++r)
+        for (int cc = 0; cc < 2; ++cc) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          if (elect_one()) {
+            uint8_t* st = tiles + stage * STAGE;
+            const uint32_t bytes = (uint32_t)(A_TILE + B_HALF) + (rm.has_lo[r] ? (uint32_t)A_TILE : 0u);
+            if (leader) mbar_expect_tx(&full[stage], 2u * bytes);
+            tma2_load_4d(st, &rm.plane[2 * r], &full[stage], cc * 64, tw * BW, th * BH, n);
+            tma2_load_2d(st + OFF_B, &rm.ident, &full[stage], cc * 64, (int)rank * 64);
+            if (rm.has_lo[r]) tma2_load_4d(st + OFF_ALO_RES, &rm.plane[2 * r + 1], &full[stage], cc * 64, tw * BW, th * BH, n);
+          }
+          __syncwarp();
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
@@ -137,7 +156,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
         const int acc = it & 1;
         mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           fence_after_sync();
@@ -163,20 +182,42 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
             phase ^= 1u;
           }
         }
+        // residuals: D2 (columns +128) = sum over planes of  plane x identity  (exact products, fp32 accumulation)
+        for (int r = 0; r < rm.nres; ++r)
+          for (int cc = 0; cc < 2; ++cc) {
+            mbar_wait(&full[stage], phase);
+            fence_after_sync();
+            if (elect_one()) {
+              const uint32_t sa = smem_u32(tiles + stage * STAGE);
+              const uint64_t a_hi = make_smem_desc(sa, 16, 1024, LAYOUT_SW128);
+              const uint64_t b_id = make_smem_desc(sa + OFF_B, 16, 1024, LAYOUT_SW128);
+              const uint64_t a_lo = make_smem_desc(sa + OFF_ALO_RES, 16, 1024, LAYOUT_SW128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma2_f16(d_tmem + 128u, a_hi + 2 * k, b_id + 2 * k, idesc, (r | cc | k) ? 1u : 0u);
+                if (rm.has_lo[r]) umma2_f16(d_tmem + 128u, a_lo + 2 * k, b_id + 2 * k, idesc, 1u);
+              }
+              umma2_commit(&empty[stage]);
+            }
+            __syncwarp();
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
         if (elect_one()) umma2_commit(&tfull[acc]);  // accumulators complete in both CTAs
         __syncwarp();
       }
     }
   } else {
     // ------------------------------------------------------------ epilogue warps 2..9 (both CTAs, own TMEM)
-    // Two warps per TMEM lane quarter, 64 columns each; the residual loads of chunk c+1 (and of the tile's
-    // first chunk, before the accumulator-full wait) are in flight while chunk c is processed.
+    // Two warps per TMEM lane quarter, 64 columns each.  Residual sums arrive in the second accumulator
+    // (columns +128) -- no global loads here.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int hl = row >> 4, wl = row & 15;
-    const bool has_r1 = p.r1h != nullptr, has_r2 = p.r2h != nullptr;
-    const bool has_r1l = p.r1l != nullptr, has_r2l = p.r2l != nullptr;
+    const bool has_res = rm.nres > 0;
     int it = 0;
     for (int pi = cid; pi < pairs; pi += nclusters, ++it) {
       const int acc = it & 1;
@@ -188,65 +229,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
       const int oy = th * BH + hl, ox = tw * BW + wl;
       const bool valid = tvalid && oy < p.OH && ox < p.OW;
       const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
-      uint4 ra[8], rb[8];
-      auto load_res = [&](int chunk, uint4 (&dst)[8]) {
-        const size_t off = pix * 128 + chunk * 16;
-        if (has_r1) {
-          dst[0] = __ldg(reinterpret_cast<const uint4*>(p.r1h + off));
-          dst[1] = __ldg(reinterpret_cast<const uint4*>(p.r1h + off) + 1);
-          if (has_r1l) {
-            dst[2] = __ldg(reinterpret_cast<const uint4*>(p.r1l + off));
-            dst[3] = __ldg(reinterpret_cast<const uint4*>(p.r1l + off) + 1);
-          }
-        }
-        if (has_r2) {
-          dst[4] = __ldg(reinterpret_cast<const uint4*>(p.r2h + off));
-          dst[5] = __ldg(reinterpret_cast<const uint4*>(p.r2h + off) + 1);
-          if (has_r2l) {
-            dst[6] = __ldg(reinterpret_cast<const uint4*>(p.r2l + off));
-            dst[7] = __ldg(reinterpret_cast<const uint4*>(p.r2l + off) + 1);
-          }
-        }
-      };
-      auto process = [&](int chunk, const uint4 (&rr)[8]) {
+      mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u);
+      fence_after_sync();
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+#pragma unroll 1
+      for (int chunk = half * 4; chunk < half * 4 + 4; ++chunk) {
         const int c0 = chunk * 16;
-        uint32_t v[16];
-        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + c0), v);
+        uint32_t v[16], r[16];
+        tmem_ld_32x16(lane_base + (uint32_t)c0, v);
+        if (has_res) tmem_ld_32x16(lane_base + 128u + (uint32_t)c0, r);
         tmem_ld_wait();
-        if (!valid) return;
+        if (!valid) continue;
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float t = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), s_scale[c0 + j]), s_shift[c0 + j]);
-          f[j] = p.act == DSIN_ACT_RELU ? fmaxf(t, 0.f) : t;
-        }
-        if (has_r1) {
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            float a[8], b[8];
-            unpack8(rr[g], a);
-            if (has_r1l) {
-              unpack8(rr[2 + g], b);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) a[e] = __fadd_rn(a[e], b[e]);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[g * 8 + e] = __fadd_rn(f[g * 8 + e], a[e]);
-          }
-        }
-        if (has_r2) {
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            float a[8], b[8];
-            unpack8(rr[4 + g], a);
-            if (has_r2l) {
-              unpack8(rr[6 + g], b);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) a[e] = __fadd_rn(a[e], b[e]);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[g * 8 + e] = __fadd_rn(f[g * 8 + e], a[e]);
-          }
+          t = p.act == DSIN_ACT_RELU ? fmaxf(t, 0.f) : t;
+          f[j] = has_res ? __fadd_rn(t, __uint_as_float(r[j])) : t;
         }
         const size_t off = pix * 128 + c0;
 #pragma unroll
@@ -264,18 +263,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
           reinterpret_cast<uint4*>(p.yh + off)[g] = uh;
           if (p.yl) reinterpret_cast<uint4*>(p.yl + off)[g] = ul;
         }
-      };
-      const int cb = half * 4;
-      if (valid) load_res(cb, ra);
-      mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u);
-      fence_after_sync();
-      if (valid) load_res(cb + 1, rb);
-      process(cb, ra);
-      if (valid) load_res(cb + 2, ra);
-      process(cb + 1, rb);
-      if (valid) load_res(cb + 3, rb);
-      process(cb + 2, ra);
-      process(cb + 3, rb);
+      }
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty[acc], 0);  // the leader's accumulator-empty barrier
@@ -286,13 +274,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
   cluster_sync_all();  // no CTA of the pair may exit (or free TMEM) while the other can still signal it
   if (warp == 1) {
     fence_after_sync();
-    tmem_dealloc2(tmem_base, 256);
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 
 template <int TERMS>
 int launch2(dsin_handle_t h, const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh,
-            const CUtensorMap& wl, const ConvTc2Args& p, cudaStream_t st) {
+            const CUtensorMap& wl, const ConvTc2Res& rm, const ConvTc2Args& p, cudaStream_t st) {
   using C = Cfg2<TERMS>;
   static bool configured = false;
   if (!configured) {
@@ -304,7 +292,7 @@ int launch2(dsin_handle_t h, const CUtensorMap& xh, const CUtensorMap& xl, const
   const int pairs = (p.total_tiles + 1) / 2;
   int clusters = h->sm_count / 2;
   if (clusters > pairs) clusters = pairs;
-  conv_tc2_kernel<TERMS><<<2 * clusters, 320, C::kSmem, st>>>(xh, xl, wh, wl, p);
+  conv_tc2_kernel<TERMS><<<2 * clusters, 320, C::kSmem, st>>>(xh, xl, wh, wl, rm, p);
   DSIN_LAUNCHED(h);
   return DSIN_OK;
 }
@@ -313,5 +301,36 @@ int launch2(dsin_handle_t h, const CUtensorMap& xh, const CUtensorMap& xl, const
 
 int conv_tc2_launch(dsin_handle_t h, int terms, const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh,
                     const CUtensorMap& wl, const ConvTc2Args& p, cudaStream_t st) {
-  return terms == 3 ? launch2<3>(h, xh, xl, wh, wl, p, st) : launch2<1>(h, xh, xl, wh, wl, p, st);
+  ConvTc2Res rm;
+  memset(&rm, 0, sizeof(rm));
+  const __half* hi[2] = {p.r1h, p.r2h};
+  const __half* lo[2] = {p.r1l, p.r2l};
+  if (hi[0] || hi[1]) {
+    if (!h->ident128) {  // one-time: 128x128 fp16 identity, the B operand that adds a residual tile on the MMA
+      std::vector<__half> eye(128 * 128, __float2half(0.f));
+      for (int i = 0; i < 128; ++i) eye[i * 128 + i] = __float2half(1.f);
+      if (cudaMalloc(&h->ident128, eye.size() * sizeof(__half)) != cudaSuccess ||
+          cudaMemcpy(h->ident128, eye.data(), eye.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess)
+        return dsin_fail(h, DSIN_ERR_CUDA, "%s: cannot create the identity slab", __func__);
+    }
+    const uint64_t id_d[2] = {128, 128};
+    const uint64_t id_s[1] = {256};
+    const uint32_t id_b[2] = {64, 64};
+    bool ok = encode_tmap(&rm.ident, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, h->ident128, id_d, id_s, id_b,
+                          CU_TENSOR_MAP_SWIZZLE_128B);
+    const uint64_t d4[4] = {128, (uint64_t)p.OW, (uint64_t)p.OH, (uint64_t)p.n};
+    const uint64_t s3[3] = {256, (uint64_t)p.OW * 256, (uint64_t)p.OH * p.OW * 256};
+    const uint32_t b4[4] = {64, BW, BH, 1};
+    for (int i = 0; i < 2; ++i) {
+      if (!hi[i]) continue;
+      const int r = rm.nres++;
+      rm.has_lo[r] = lo[i] != nullptr;
+      ok = ok && encode_tmap(&rm.plane[2 * r], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, hi[i], d4, s3, b4,
+                             CU_TENSOR_MAP_SWIZZLE_128B);
+      ok = ok && encode_tmap(&rm.plane[2 * r + 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, lo[i] ? lo[i] : hi[i], d4, s3,
+                             b4, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
+    if (!ok) return dsin_fail(h, DSIN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", __func__);
+  }
+  return terms == 3 ? launch2<3>(h, xh, xl, wh, wl, rm, p, st) : launch2<1>(h, xh, xl, wh, wl, rm, p, st);
 }
