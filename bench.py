@@ -175,6 +175,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         g.build()
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     if rank != 0:
