@@ -28,6 +28,11 @@ class SiNet(object):
         self._tc = None
         self.device = "cuda"
 
+    def clone(self):
+        """A fresh instance: every AE owns its SI-Net variables (as every TF graph of the reference does), so
+        loading weights into one AE never invalidates what another AE's captured CUDA graphs point at."""
+        return type(self)()
+
     def load_weights(self, W):
         S = synth.SIN
         layers = []

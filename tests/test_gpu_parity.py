@@ -583,3 +583,30 @@ def test_tf_checkpoint_save_restore_and_main_drop_in(tmp_path, monkeypatch):
                               np.clip(np.array(xsi[0]), 0, 255).transpose(1, 2, 0).astype("uint8"))
     for name in ("bpp_list_", "l1_list_", "psnr_list_", "msssim_list_", "mse_list_x_y_syn_", "avg_Pearson_list_x_y_syn_"):
         assert len(open(str(tmp_path / "images" / (name + "tiny_model.txt"))).read().split()) == 2
+
+
+def test_cuda_graph_replay_equals_eager_and_follows_weight_reload():
+    """The numpy entry point replays two captured CUDA graphs; results must be bit-identical to the eager
+    launch sequence, for changing inputs, and a weight reload must invalidate the captured graphs."""
+    ae = make_ae(80, 144, calibrated_weights(0))
+    assert ae.use_cuda_graph
+    pairs = [synth.make_batch(2, 80, 144, seed=s) for s in (3, 4)]
+    got = []
+    for x, y in pairs:                      # first call captures, second replays with new inputs
+        got.append([np.array(a) for a in ae.siNet_get_reconstructed(x.astype(np.uint8), y.astype(np.uint8))])
+    assert len(ae._graphs) == 1
+    ae.use_cuda_graph = False
+    for (x, y), g in zip(pairs, got):
+        ref = ae.siNet_get_reconstructed(x.astype(np.uint8), y.astype(np.uint8))
+        for a, b in zip(ref, g):
+            assert np.array_equal(np.array(a), b)
+    ae.use_cuda_graph = True
+    ae.set_weights(calibrated_weights(1))
+    assert not ae._graphs
+    x, y = pairs[0]
+    new = [np.array(a) for a in ae.siNet_get_reconstructed(x, y)]
+    assert not np.array_equal(new[2], got[0][2])          # different weights -> different x_dec
+    ae.use_cuda_graph = False
+    ref = ae.siNet_get_reconstructed(x, y)
+    for a, b in zip(ref, new):
+        assert np.array_equal(np.array(a), b)
