@@ -139,7 +139,8 @@ def run_reference(args, rank):
     sec = float(np.mean(times))
     mpix = H * W * 1e-6 / sec
     line = {
-        "impl": "reference", "metric": METRIC, "value": mpix, "unit": "Mpixels/s", "n_gpus": 0,
+        "impl": "reference", "metric": METRIC, "value": mpix, "unit": "Mpixels/s", "n_gpus": args.gpus,
+        "gpus_used": 0,
         "steps": steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "full inference (AE(y)+AE(x)+bpp+SI-Finder+SI-Net), 1 pair of 320x1224 per step; "

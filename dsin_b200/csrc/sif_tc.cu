@@ -121,7 +121,9 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (converged warp, one lane issues)
     {
-      constexpr uint32_t idesc = make_idesc_f16(128, TN, 0);
+      constexpr uint32_t idesc_full = make_idesc_f16(128, TN, 0);
+      // the last tile of a correlation row holds wp - (jtiles-1)*TN positions: issue only that many columns
+      const uint32_t idesc_last = make_idesc_f16(128, ((p.wp - (p.jtiles - 1) * TN) + 15) & ~15, 0);
       int stage = 0, it = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
@@ -133,6 +135,7 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
             fence_after_sync();
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * TN;
+            const uint32_t idesc = jt == p.jtiles - 1 ? idesc_last : idesc_full;
             for (int d = 0; d < PAIRS; ++d) {
               mbar_wait(&full[stage], phase);
               fence_after_sync();
