@@ -60,6 +60,9 @@ SIGNATURES = {
     "dsin_msssim_workspace_bytes": (_I64, [_I, _I, _I, _I, _I]),
     "dsin_msssim": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "dsin_sif_gather": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "dsin_pc_codec_workspace_bytes": (_I64, [_I, _I, _I, _I]),
+    "dsin_pc_encode": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _I64, _P, _P, _P, _P]),
+    "dsin_pc_decode": (_I, [_P, _P, _I64, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P]),
 }
 
 _lib = None

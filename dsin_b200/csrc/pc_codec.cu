@@ -1,0 +1,541 @@
+// PC1 entropy coder on the GPU: real bitstreams from the probability model.
+//
+// The reference only ships the pieces of a coder (src/probclass_imgcomp.py:361-482: one symbol at a time, each with
+// the frequencies the context model predicts from the symbols already coded).  The bit-exact definition this kernel
+// implements -- operation order of the fp32 network, frequency quantisation, range coder, symbol order -- is written
+// down in oracle/pc_codec.c; the two must produce identical bytes.
+//
+// Parallel schedule.  The receptive field of the four masked (2,3,3) convolutions (probclass_imgcomp.py:150-176,
+// 214-261) reaches one step back per layer, so position p = (d, h, w) of every layer only needs positions whose
+// wavefront time 25 d + 5 h + w is smaller.  One CTA owns one stream = the depth slices d == stream (mod nstreams)
+// and walks a slice in steps of u = 5 h + w (<= 33 positions per step); per step: layer 0, 1, 2, logits, frequency
+// tables in parallel over (position, channel), then one thread runs the range coder over the step's symbols.
+// Slice d may run u + 6 steps behind slice d - 1 (another CTA of the same image): a per-slice progress counter in
+// global memory (release / acquire) is the only inter-CTA synchronisation, so the slices of an image form a
+// software pipeline across its CTAs.  All CTAs of a launch must be co-resident (cooperative launch).
+//
+// Determinism.  Every activation is an fmaf chain in the order of oracle/pc_codec.c (bias; live taps in raster
+// order; input channels ascending); exp is a fixed polynomial; only correctly rounded IEEE operations are used.
+#include "common.cuh"
+
+namespace {
+
+constexpr int K = 24;          // hidden channels
+constexpr int KP = 28;         // padded channel stride of the transposed weights in shared memory (conflict-free LDS.128)
+constexpr int MAXL = 8;        // centres
+constexpr int NT0 = 13, NT = 14;
+constexpr int MAXPOS = 33;
+constexpr int THREADS = 800;   // 33 positions x 24 channels = 792
+constexpr uint32_t TOTAL_BITS = 16, TOTAL = 1u << TOTAL_BITS;
+constexpr int PROGRESS_INIT = -1000000;
+
+__constant__ int c_taps[NT][3] = {{-1, -1, -1}, {-1, -1, 0}, {-1, -1, 1}, {-1, 0, -1}, {-1, 0, 0}, {-1, 0, 1}, {-1, 1, -1},
+                                  {-1, 1, 0},   {-1, 1, 1},  {0, -1, -1}, {0, -1, 0}, {0, -1, 1}, {0, 0, -1}, {0, 0, 0}};
+
+struct CodecArgs {
+  int n, C, H, W, L, nstreams, decode, reset_status;
+  const float* centers;
+  const float *w0, *b0, *w1, *b1, *w2, *b2, *w3, *b3;
+  float* q;        // [n][C][H+8][W+8]
+  float* a0;       // [n][C][H+6][W+6][K]
+  float* a1;       // [n][C][H+4][W+4][K]
+  float* a2;       // [n][C][H+2][W+2][K]
+  int* progress;   // [n][C]
+  int64_t* sym;    // [n][C][H][W]   (input when encoding, output when decoding)
+  uint8_t* bytes;  // [n][nstreams][cap]
+  int64_t cap;
+  int64_t* sizes;  // [n][nstreams]
+  int* status;     // != 0: a stream overflowed its capacity
+};
+
+__device__ __forceinline__ float relu(float x) { return x > 0.0f ? x : 0.0f; }
+
+__device__ __forceinline__ float exp_det(float x) {
+  if (x < -80.0f) x = -80.0f;
+  const float t = __fmul_rn(x, 1.4426950408889634f);
+  const float n = floorf(t);
+  const float f = __fsub_rn(t, n);
+  float p = 1.5353362e-4f;
+  p = __fmaf_rn(p, f, 1.3398874e-3f);
+  p = __fmaf_rn(p, f, 9.6184370e-3f);
+  p = __fmaf_rn(p, f, 5.5503324e-2f);
+  p = __fmaf_rn(p, f, 2.4022648e-1f);
+  p = __fmaf_rn(p, f, 6.9314720e-1f);
+  p = __fmaf_rn(p, f, 1.0f);
+  return __fmul_rn(p, __uint_as_float((uint32_t)((int)n + 127) << 23));
+}
+
+__device__ __forceinline__ void logits_to_freqs(const float* l, int L, uint32_t* f) {
+  float m = l[0];
+  int am = 0;
+  for (int i = 1; i < L; ++i)
+    if (l[i] > m) { m = l[i]; am = i; }
+  float e[MAXL], Z = 0.0f;
+  for (int i = 0; i < L; ++i) {
+    e[i] = exp_det(__fsub_rn(l[i], m));
+    Z = __fadd_rn(Z, e[i]);
+  }
+  const float scale = __fdiv_rn((float)(TOTAL - (uint32_t)L), Z);
+  uint32_t sum = 0;
+  for (int i = 0; i < L; ++i) {
+    f[i] = 1u + (uint32_t)__fmul_rn(e[i], scale);
+    sum += f[i];
+  }
+  f[am] += TOTAL - sum;
+}
+
+// ---------------------------------------------------------------- range coder (one thread per stream)
+struct RcEnc {
+  uint64_t low;
+  uint32_t range;
+  uint32_t cache;
+  uint64_t cache_size;
+  uint8_t* out;
+  int64_t pos, cap;
+  int overflow, skip_first;
+  __device__ void init(uint8_t* o, int64_t c) {
+    low = 0; range = 0xFFFFFFFFu; cache = 0; cache_size = 1; out = o; pos = 0; cap = c; overflow = 0; skip_first = 1;
+  }
+  __device__ void put(uint8_t b) {
+    if (skip_first) { skip_first = 0; return; }
+    if (pos < cap) out[pos] = b; else overflow = 1;
+    pos++;
+  }
+  __device__ void shift_low() {
+    if ((uint32_t)low < 0xFF000000u || (low >> 32) != 0) {
+      const uint8_t carry = (uint8_t)(low >> 32);
+      uint8_t c = (uint8_t)cache;
+      do {
+        put((uint8_t)(c + carry));
+        c = 0xFF;
+      } while (--cache_size != 0);
+      cache = (uint32_t)((low >> 24) & 0xFF);
+    }
+    cache_size++;
+    low = (low & 0x00FFFFFFull) << 8;
+  }
+  __device__ void encode(uint32_t cum, uint32_t freq) {
+    const uint32_t r = range >> TOTAL_BITS;
+    low += (uint64_t)r * cum;
+    range = r * freq;
+    while (range < (1u << 24)) { range <<= 8; shift_low(); }
+  }
+  __device__ void flush() {
+    const uint64_t hi = low + range - 1;
+    int k = 4;
+    uint64_t v = 0;
+    for (; k >= 0; --k) {
+      v = hi & ~((1ull << (8 * k)) - 1);
+      if (v >= low) break;
+    }
+    low = v;
+    for (int i = 0; i < 5 - k; ++i) shift_low();
+  }
+};
+
+constexpr int WIN = 128;  // bytes of the stream staged per step (a step consumes <= 2 bytes per symbol)
+struct RcDec {
+  uint32_t code, range;
+  const uint8_t* in;
+  int64_t pos, len;
+  const uint8_t* win;   // shared-memory copy of in[wbase, wbase + WIN)
+  int64_t wbase;
+  __device__ uint8_t get() {
+    const int64_t o = pos - wbase;
+    const uint8_t b = pos >= len ? 0 : (o >= 0 && o < WIN ? win[o] : in[pos]);
+    pos++;
+    return b;
+  }
+  __device__ void init(const uint8_t* i, int64_t l, const uint8_t* w) {
+    in = i; pos = 0; len = l; range = 0xFFFFFFFFu; code = 0; win = w; wbase = -WIN;
+    for (int k = 0; k < 4; ++k) code = (code << 8) | get();
+  }
+  __device__ int decode(const uint32_t* f, int L) {
+    const uint32_t r = range >> TOTAL_BITS;
+    uint32_t v = code / r;
+    if (v > TOTAL - 1) v = TOTAL - 1;
+    uint32_t cum = 0;
+    int s = 0;
+    while (s < L - 1 && cum + f[s] <= v) { cum += f[s]; ++s; }
+    code -= cum * r;
+    range = r * f[s];
+    while (range < (1u << 24)) { code = (code << 8) | get(); range <<= 8; }
+    return s;
+  }
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// one output channel of a 24-input layer at one position: bias, then 14 taps x 24 channels in order.
+// src(t) returns the 24 input channels of tap t (global, L2-coherent loads) or nullptr for the constant vector.
+template <typename Src>
+__device__ __forceinline__ float dot24(float acc, const float* __restrict__ wt /* [NT][cout][KP], this co */, int cout_stride,
+                                       const float* __restrict__ kconst, Src src) {
+#pragma unroll 1
+  for (int t = 0; t < NT; ++t) {
+    const float* x = src(t);
+    const float4* w4 = reinterpret_cast<const float4*>(wt + (size_t)t * cout_stride);
+    if (x != nullptr) {
+      const float4* x4 = reinterpret_cast<const float4*>(x);
+#pragma unroll
+      for (int g = 0; g < K / 4; ++g) {
+        const float4 xv = __ldcg(x4 + g);
+        const float4 wv = w4[g];
+        acc = __fmaf_rn(xv.x, wv.x, acc);
+        acc = __fmaf_rn(xv.y, wv.y, acc);
+        acc = __fmaf_rn(xv.z, wv.z, acc);
+        acc = __fmaf_rn(xv.w, wv.w, acc);
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < K / 4; ++g) {
+        const float4 wv = w4[g];
+        acc = __fmaf_rn(kconst[4 * g + 0], wv.x, acc);
+        acc = __fmaf_rn(kconst[4 * g + 1], wv.y, acc);
+        acc = __fmaf_rn(kconst[4 * g + 2], wv.z, acc);
+        acc = __fmaf_rn(kconst[4 * g + 3], wv.w, acc);
+      }
+    }
+  }
+  return acc;
+}
+
+// the same chain with the inputs of all 14 taps staged in shared memory ([NT][K] floats of this position)
+__device__ __forceinline__ float dot24_staged(float acc, const float* __restrict__ wt, int cout_stride,
+                                              const float* __restrict__ xin) {
+#pragma unroll 2
+  for (int t = 0; t < NT; ++t) {
+    const float4* w4 = reinterpret_cast<const float4*>(wt + (size_t)t * cout_stride);
+    const float4* x4 = reinterpret_cast<const float4*>(xin + t * K);
+#pragma unroll
+    for (int g = 0; g < K / 4; ++g) {
+      const float4 xv = x4[g];
+      const float4 wv = w4[g];
+      acc = __fmaf_rn(xv.x, wv.x, acc);
+      acc = __fmaf_rn(xv.y, wv.y, acc);
+      acc = __fmaf_rn(xv.z, wv.z, acc);
+      acc = __fmaf_rn(xv.w, wv.w, acc);
+    }
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) pc_codec_kernel(const CodecArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_w1 = smem;                       // [NT][K][KP]   transposed: (tap, co, ci)
+  float* s_w2 = s_w1 + NT * K * KP;         // [NT][K][KP]
+  float* s_w3 = s_w2 + NT * K * KP;         // [NT][MAXL][KP]
+  float* s_w0 = s_w3 + NT * MAXL * KP;      // [NT0][K]
+  float* s_b0 = s_w0 + NT0 * K;             // [K] x 3, [MAXL]
+  float* s_b1 = s_b0 + K;
+  float* s_b2 = s_b1 + K;
+  float* s_b3 = s_b2 + K;
+  float* s_k0 = s_b3 + MAXL;                // constant activations of the padding-only slices d < 0
+  float* s_k1 = s_k0 + K;
+  float* s_k2 = s_k1 + K;
+  float* s_cent = s_k2 + K;                 // [MAXL]
+  float* s_logit = s_cent + MAXL;           // [MAXPOS][MAXL]
+  uint32_t* s_freq = reinterpret_cast<uint32_t*>(s_logit + MAXPOS * MAXL);  // [MAXPOS][MAXL]
+  float* s_in = reinterpret_cast<float*>(s_freq + MAXPOS * MAXL);           // [MAXPOS][NT][K] staged layer inputs
+  int* s_sym = reinterpret_cast<int*>(s_in + MAXPOS * NT * K);              // [MAXPOS] symbols of the step (encode)
+  long long* s_pos = reinterpret_cast<long long*>(s_sym + MAXPOS + 1);      // decoder read position (8-byte aligned)
+  uint8_t* s_win = reinterpret_cast<uint8_t*>(s_pos + 1);                   // [WIN] stream bytes of the step (decode)
+
+  const int tid = threadIdx.x;
+  const int img = blockIdx.x / p.nstreams, stream = blockIdx.x % p.nstreams;
+  const int C = p.C, H = p.H, W = p.W, L = p.L;
+  const float pad = p.centers[0];
+
+  // ---- stage the weights (transposed to (tap, co, ci), ci padded to KP) and the constants
+  for (int i = tid; i < NT * K * KP; i += THREADS) {
+    const int ci = i % KP, co = (i / KP) % K, t = i / (KP * K);
+    s_w1[i] = ci < K ? p.w1[((size_t)t * K + ci) * K + co] : 0.f;
+    s_w2[i] = ci < K ? p.w2[((size_t)t * K + ci) * K + co] : 0.f;
+  }
+  for (int i = tid; i < NT * MAXL * KP; i += THREADS) {
+    const int ci = i % KP, co = (i / KP) % MAXL, t = i / (KP * MAXL);
+    s_w3[i] = (ci < K && co < L) ? p.w3[((size_t)t * K + ci) * L + co] : 0.f;
+  }
+  for (int i = tid; i < NT0 * K; i += THREADS) s_w0[i] = p.w0[i];
+  if (tid < K) { s_b0[tid] = p.b0[tid]; s_b1[tid] = p.b1[tid]; s_b2[tid] = p.b2[tid]; }
+  if (tid < MAXL) { s_b3[tid] = tid < L ? p.b3[tid] : 0.f; s_cent[tid] = tid < L ? p.centers[tid] : 0.f; }
+  __syncthreads();
+  if (tid < K) {
+    float acc = s_b0[tid];
+    for (int t = 0; t < NT0; ++t) acc = __fmaf_rn(pad, s_w0[t * K + tid], acc);
+    s_k0[tid] = relu(acc);
+  }
+  __syncthreads();
+  if (tid < K) s_k1[tid] = relu(dot24(s_b1[tid], s_w1 + tid * KP, K * KP, s_k0, [](int) { return (const float*)nullptr; }));
+  __syncthreads();
+  if (tid < K)
+    s_k2[tid] = __fadd_rn(dot24(s_b2[tid], s_w2 + tid * KP, K * KP, s_k1, [](int) { return (const float*)nullptr; }), s_k0[tid]);
+  __syncthreads();
+
+  // ---- volumes of this image
+  const size_t q_plane = (size_t)(H + 8) * (W + 8);
+  const size_t a0_plane = (size_t)(H + 6) * (W + 6) * K, a1_plane = (size_t)(H + 4) * (W + 4) * K,
+               a2_plane = (size_t)(H + 2) * (W + 2) * K;
+  float* q = p.q + (size_t)img * C * q_plane;
+  float* a0 = p.a0 + (size_t)img * C * a0_plane;
+  float* a1 = p.a1 + (size_t)img * C * a1_plane;
+  float* a2 = p.a2 + (size_t)img * C * a2_plane;
+  int* progress = p.progress + (size_t)img * C;
+  int64_t* sym = p.sym + (size_t)img * C * H * W;
+  auto q_at = [&](int d, int h, int w) { return q + (size_t)d * q_plane + (size_t)(h + 4) * (W + 8) + (w + 4); };
+  auto a0_at = [&](int d, int h, int w) { return a0 + (size_t)d * a0_plane + ((size_t)(h + 3) * (W + 6) + (w + 3)) * K; };
+  auto a1_at = [&](int d, int h, int w) { return a1 + (size_t)d * a1_plane + ((size_t)(h + 2) * (W + 4) + (w + 2)) * K; };
+  auto a2_at = [&](int d, int h, int w) { return a2 + (size_t)d * a2_plane + ((size_t)(h + 1) * (W + 2) + (w + 1)) * K; };
+
+  RcEnc enc;
+  RcDec dec;
+  if (tid == 0) {
+    uint8_t* base = p.bytes + ((size_t)img * p.nstreams + stream) * p.cap;
+    if (p.decode) {
+      dec.init(base, p.sizes[(size_t)img * p.nstreams + stream], s_win);
+      *s_pos = dec.pos;
+    } else {
+      enc.init(base, p.cap);
+    }
+  }
+  const uint8_t* my_stream = p.bytes + ((size_t)img * p.nstreams + stream) * p.cap;
+  const int64_t my_len = p.decode ? p.sizes[(size_t)img * p.nstreams + stream] : 0;
+
+  const int j = tid / K, co = tid % K;     // (position, channel) of the 24-channel layers
+  const int jl = tid / MAXL, il = tid % MAXL;  // (position, logit)
+  const int u_min = 5 * -3 - 3, u_max = 5 * (H + 2) + (W + 2);
+
+  for (int d = stream; d < C; d += p.nstreams) {
+    for (int u = u_min; u <= u_max; ++u) {
+      // positions of this step: h in [h_lo, h_hi], w = u - 5 h in [-3, W+2]
+      int h_lo = u - (W + 2);
+      h_lo = h_lo > 0 ? (h_lo + 4) / 5 : -((-h_lo) / 5);  // ceil(h_lo / 5)
+      if (h_lo < -3) h_lo = -3;
+      int h_hi = u + 3;
+      h_hi = h_hi >= 0 ? h_hi / 5 : -((-h_hi + 4) / 5);   // floor((u + 3) / 5)
+      if (h_hi > H + 2) h_hi = H + 2;
+      const int npos = h_hi - h_lo + 1;
+      if (d > 0 && tid == 0) {  // slice d - 1 must be complete through step u + 6
+        const int need = u + 6 < u_max ? u + 6 : u_max;
+        while (ld_acquire(progress + d - 1) < need) __nanosleep(64);
+        __threadfence();
+      }
+      __syncthreads();
+      const int h = h_lo + j, w = u - 5 * h;
+      const bool act = j < npos;
+      // ---- layer 0: 13 taps of q (1 channel)
+      if (act) {
+        float acc = s_b0[co];
+#pragma unroll
+        for (int t = 0; t < NT0; ++t) {
+          const int dd = d + c_taps[t][0];
+          const float x = dd < 0 ? pad : __ldcg(q_at(dd, h + c_taps[t][1], w + c_taps[t][2]));
+          acc = __fmaf_rn(x, s_w0[t * K + co], acc);
+        }
+        a0_at(d, h, w)[co] = relu(acc);
+      }
+      __syncthreads();
+      // One L2 round trip per layer: all threads gather the 14 x 24 inputs of every position of the step into
+      // shared memory (constant vector for the padding-only slices d < 0), then each (position, channel)
+      // thread runs its fmaf chain out of shared memory.
+      auto gather = [&](auto at_fn, const float* kconst, int lo, int hiH, int hiW) {
+        const float4* k4 = reinterpret_cast<const float4*>(kconst);
+        float4* dst = reinterpret_cast<float4*>(s_in);
+        for (int idx = tid; idx < npos * NT * (K / 4); idx += THREADS) {
+          const int jj = idx / (NT * (K / 4)), r = idx % (NT * (K / 4));
+          const int t = r / (K / 4), g = r % (K / 4);
+          const int hh = h_lo + jj, ww = u - 5 * hh;
+          if (hh < lo || hh >= hiH || ww < lo || ww >= hiW) continue;
+          // tap offsets computed, not looked up: a thread-varying index into constant memory would serialise
+          const int dd = t < 9 ? d - 1 : d;
+          const int dh = t < 9 ? t / 3 - 1 : (t < 12 ? -1 : 0);
+          const int dw = t < 9 ? t % 3 - 1 : (t < 12 ? t - 10 : t - 13);
+          dst[idx] = dd < 0 ? k4[g] : __ldcg(reinterpret_cast<const float4*>(at_fn(dd, hh + dh, ww + dw)) + g);
+        }
+      };
+      // ---- layer 1
+      gather(a0_at, s_k0, -2, H + 2, W + 2);
+      __syncthreads();
+      if (act && h >= -2 && h < H + 2 && w >= -2 && w < W + 2)
+        a1_at(d, h, w)[co] = relu(dot24_staged(s_b1[co], s_w1 + co * KP, K * KP, s_in + j * NT * K));
+      __syncthreads();
+      // ---- layer 2 (+ skip)
+      gather(a1_at, s_k1, -1, H + 1, W + 1);
+      __syncthreads();
+      if (act && h >= -1 && h < H + 1 && w >= -1 && w < W + 1)
+        a2_at(d, h, w)[co] = __fadd_rn(dot24_staged(s_b2[co], s_w2 + co * KP, K * KP, s_in + j * NT * K),
+                                       __ldcg(a0_at(d, h, w) + co));
+      __syncthreads();
+      // ---- logits
+      gather(a2_at, s_k2, 0, H, W);
+      __syncthreads();
+      {
+        const int hl = h_lo + jl, wl = u - 5 * hl;
+        if (jl < npos && il < L && hl >= 0 && hl < H && wl >= 0 && wl < W)
+          s_logit[jl * MAXL + il] = relu(dot24_staged(s_b3[il], s_w3 + il * KP, MAXL * KP, s_in + jl * NT * K));
+      }
+      __syncthreads();
+      // ---- frequency tables, one thread per position; the coder's global reads are staged by other threads
+      if (tid < npos) {
+        const int hf = h_lo + tid, wf = u - 5 * hf;
+        if (hf >= 0 && hf < H && wf >= 0 && wf < W) {
+          logits_to_freqs(s_logit + tid * MAXL, L, s_freq + tid * MAXL);
+          if (!p.decode) s_sym[tid] = (int)sym[((size_t)d * H + hf) * W + wf];
+        }
+      } else if (p.decode && tid >= 64 && tid < 64 + WIN) {
+        const int64_t at = (int64_t)*s_pos + (tid - 64);
+        s_win[tid - 64] = at < my_len ? my_stream[at] : 0;
+      }
+      __syncthreads();
+      // ---- range coder over the step's symbols (increasing h), publish the step
+      if (tid == 0) {
+        if (p.decode) dec.wbase = *s_pos;
+        for (int jj = 0; jj < npos; ++jj) {
+          const int hc = h_lo + jj, wc = u - 5 * hc;
+          if (hc < 0 || hc >= H || wc < 0 || wc >= W) continue;
+          const uint32_t* f = s_freq + jj * MAXL;
+          int64_t* sp = sym + ((size_t)d * H + hc) * W + wc;
+          int s;
+          if (p.decode) {
+            s = dec.decode(f, L);
+            *sp = s;
+            *q_at(d, hc, wc) = s_cent[s];
+          } else {
+            s = s_sym[jj];
+            uint32_t cum = 0;
+            for (int i = 0; i < s; ++i) cum += f[i];
+            enc.encode(cum, f[s]);
+          }
+        }
+        if (p.decode) *s_pos = dec.pos;
+        __threadfence();
+        st_release(progress + d, u);
+      }
+      // the barrier at the top of the next step orders the coder's q writes before the next layer-0 reads
+    }
+  }
+  if (tid == 0 && !p.decode) {
+    enc.flush();
+    p.sizes[(size_t)img * p.nstreams + stream] = enc.pos;
+    if (enc.overflow) atomicExch(p.status, 1);
+  }
+}
+
+// q volume with its halo: centres of the symbols (encode) or the pad value everywhere (decode); progress reset
+__global__ void pc_codec_prepare_kernel(CodecArgs p) {
+  const size_t plane = (size_t)(p.H + 8) * (p.W + 8);
+  const size_t total = (size_t)p.n * p.C * plane;
+  const float pad = p.centers[0];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % (p.W + 8)) - 4, h = (int)((i / (p.W + 8)) % (p.H + 8)) - 4;
+    const size_t nd = i / plane;
+    float v = pad;
+    if (!p.decode && h >= 0 && h < p.H && w >= 0 && w < p.W) {
+      const int64_t s = p.sym[(nd * p.H + h) * p.W + w];
+      v = p.centers[s >= 0 && s < p.L ? s : 0];
+    }
+    p.q[i] = v;
+  }
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid < (size_t)p.n * p.C) p.progress[gid] = PROGRESS_INIT;
+  if (gid == 0 && p.reset_status) *p.status = 0;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct Layout {
+  size_t q, a0, a1, a2, progress, total;
+};
+Layout layout(int n, int c, int h, int w) {
+  Layout l;
+  size_t off = 0;
+  l.q = off; off += align256((size_t)n * c * (h + 8) * (w + 8) * sizeof(float));
+  l.a0 = off; off += align256((size_t)n * c * (h + 6) * (w + 6) * K * sizeof(float));
+  l.a1 = off; off += align256((size_t)n * c * (h + 4) * (w + 4) * K * sizeof(float));
+  l.a2 = off; off += align256((size_t)n * c * (h + 2) * (w + 2) * K * sizeof(float));
+  l.progress = off; off += align256((size_t)n * c * sizeof(int));
+  l.total = off;
+  return l;
+}
+
+constexpr size_t kSmemBytes =
+    (size_t)(2 * NT * K * KP + NT * MAXL * KP + NT0 * K + 3 * K + MAXL + 3 * K + MAXL + MAXPOS * MAXL) * sizeof(float) +
+    (size_t)MAXPOS * MAXL * sizeof(uint32_t) + (size_t)MAXPOS * NT * K * sizeof(float) +
+    (size_t)(MAXPOS + 1) * sizeof(int) + sizeof(long long) + WIN;
+
+int run_codec(dsin_handle_t h, int decode, int64_t* symbols, int n, int c, int hh, int ww, const float* centers, int L,
+              const float* const* wb, int k, int nstreams, uint8_t* bytes, int64_t cap, int64_t* sizes, int* status_out,
+              void* workspace, cudaStream_t st) {
+  DSIN_REQUIRE(h, symbols && centers && wb && bytes && sizes && workspace && status_out, "null pointer");
+  DSIN_REQUIRE(h, n > 0 && c > 0 && hh > 0 && ww > 0 && cap > 0, "bad shape");
+  DSIN_REQUIRE(h, k == K, "the codec is built for 24 hidden channels");
+  DSIN_REQUIRE(h, L >= 2 && L <= MAXL, "2..8 centres");
+  DSIN_REQUIRE(h, nstreams >= 1 && nstreams <= 64, "1..64 streams per image");
+  DSIN_REQUIRE(h, (ww + 5) / 5 + 1 <= MAXPOS, "volume wider than 159 symbols (one CTA walks a slice 33 positions at a time)");
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(pc_codec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+      return dsin_fail(h, DSIN_ERR_CUDA, "%s: cannot raise dynamic shared memory", __func__);
+    configured = true;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pc_codec_kernel, THREADS, kSmemBytes) != cudaSuccess || per_sm < 1)
+    return dsin_fail(h, DSIN_ERR_CUDA, "%s: kernel does not fit an SM", __func__);
+  const int resident = per_sm * h->sm_count;
+  DSIN_REQUIRE(h, nstreams <= resident, "more streams than co-resident CTAs");
+  const int imgs_per_launch = resident / nstreams;
+  for (int i0 = 0; i0 < n; i0 += imgs_per_launch) {
+    const int ni = n - i0 < imgs_per_launch ? n - i0 : imgs_per_launch;
+    const Layout l = layout(ni, c, hh, ww);
+    CodecArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = ni; a.C = c; a.H = hh; a.W = ww; a.L = L; a.nstreams = nstreams; a.decode = decode;
+    a.centers = centers;
+    a.w0 = wb[0]; a.b0 = wb[1]; a.w1 = wb[2]; a.b1 = wb[3]; a.w2 = wb[4]; a.b2 = wb[5]; a.w3 = wb[6]; a.b3 = wb[7];
+    uint8_t* ws = (uint8_t*)workspace;
+    a.q = (float*)(ws + l.q); a.a0 = (float*)(ws + l.a0); a.a1 = (float*)(ws + l.a1); a.a2 = (float*)(ws + l.a2);
+    a.progress = (int*)(ws + l.progress); a.status = status_out; a.reset_status = i0 == 0;
+    a.sym = symbols + (size_t)i0 * c * hh * ww;
+    a.bytes = bytes + (size_t)i0 * nstreams * cap; a.cap = cap; a.sizes = sizes + (size_t)i0 * nstreams;
+    pc_codec_prepare_kernel<<<h->sm_count * 4, 256, 0, st>>>(a);
+    DSIN_LAUNCHED(h);
+    void* params[] = {&a};
+    if (cudaLaunchCooperativeKernel((const void*)pc_codec_kernel, dim3(ni * nstreams), dim3(THREADS), params, kSmemBytes,
+                                    st) != cudaSuccess)
+      return dsin_fail(h, DSIN_ERR_CUDA, "%s: cooperative launch failed (are all CTAs co-resident?)", __func__);
+    DSIN_LAUNCHED(h);
+  }
+  return DSIN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t dsin_pc_codec_workspace_bytes(int n, int c, int hh, int ww) {
+  if (n <= 0 || c <= 0 || hh <= 0 || ww <= 0) return -1;
+  return (int64_t)layout(n, c, hh, ww).total;
+}
+
+int dsin_pc_encode(dsin_handle_t h, const int64_t* symbols, int n, int c, int hh, int ww, const float* centers, int L,
+                   const float* const* weights, int k, int nstreams, uint8_t* bytes, int64_t cap, int64_t* sizes,
+                   int* status, void* workspace, void* stream) {
+  return run_codec(h, 0, const_cast<int64_t*>(symbols), n, c, hh, ww, centers, L, weights, k, nstreams, bytes, cap, sizes,
+                   status, workspace, (cudaStream_t)stream);
+}
+
+int dsin_pc_decode(dsin_handle_t h, const uint8_t* bytes, int64_t cap, const int64_t* sizes, int n, int c, int hh, int ww,
+                   const float* centers, int L, const float* const* weights, int k, int nstreams, int64_t* symbols,
+                   int* status, void* workspace, void* stream) {
+  return run_codec(h, 1, symbols, n, c, hh, ww, centers, L, weights, k, nstreams, const_cast<uint8_t*>(bytes), cap,
+                   const_cast<int64_t*>(sizes), status, workspace, (cudaStream_t)stream);
+}
+
+}  // extern "C"

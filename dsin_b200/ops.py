@@ -450,3 +450,51 @@ def msssim(img1_nhwc, img2_nhwc, form="standard"):
     lv = lv.cpu().numpy()
     w = np.array(MSSSIM_WEIGHTS)
     return np.prod(lv[:, :4, 1] ** w[:4], axis=1) * (lv[:, 4, 0] ** w[4])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PC1 entropy coder (csrc/pc_codec.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def _pc_codec_ptrs(wlist):
+    import ctypes as C
+    arr = (C.c_void_p * 8)(*[t.data_ptr() for t in wlist])
+    return arr
+
+
+def pc_stream_capacity(c, hh, ww, nstreams):
+    """Bytes that always hold one stream: <= 16 bits per symbol (every frequency is >= 1 of 65536) + flush."""
+    slices = (c + nstreams - 1) // nstreams
+    return 2 * slices * hh * ww + 16
+
+
+def pc_encode(symbols, centers, wlist, nstreams=8):
+    """symbols (n,c,h,w) int64 CUDA -> (bytes (n,nstreams,cap) uint8, sizes (n,nstreams) int64, status int32[1])."""
+    h = handle()
+    n, c, hh, ww = symbols.shape
+    dev = symbols.device
+    cap = pc_stream_capacity(c, hh, ww, nstreams)
+    out = torch.zeros((n, nstreams, cap), dtype=torch.uint8, device=dev)
+    sizes = torch.zeros((n, nstreams), dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(int(h.lib.dsin_pc_codec_workspace_bytes(n, c, hh, ww)), dtype=torch.uint8, device=dev)
+    ptrs = _pc_codec_ptrs(wlist)
+    h.check(h.lib.dsin_pc_encode(h.ptr, _p(_chk(symbols, torch.int64)), n, c, hh, ww, _p(_chk(centers)), int(centers.numel()),
+                                 ptrs, int(wlist[1].numel()), nstreams, _p(out), cap, _p(sizes), _p(status), _p(ws),
+                                 _stream()))
+    return out, sizes, status
+
+
+def pc_decode(stream_bytes, sizes, shape, centers, wlist):
+    """stream_bytes (n,nstreams,cap) uint8 CUDA, sizes (n,nstreams) int64 CUDA -> symbols (n,c,h,w) int64."""
+    h = handle()
+    n, c, hh, ww = shape
+    dev = stream_bytes.device
+    nstreams, cap = int(stream_bytes.shape[1]), int(stream_bytes.shape[2])
+    sym = torch.zeros((n, c, hh, ww), dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(int(h.lib.dsin_pc_codec_workspace_bytes(n, c, hh, ww)), dtype=torch.uint8, device=dev)
+    ptrs = _pc_codec_ptrs(wlist)
+    h.check(h.lib.dsin_pc_decode(h.ptr, _p(_chk(stream_bytes, torch.uint8)), cap, _p(_chk(sizes, torch.int64)), n, c, hh, ww,
+                                 _p(_chk(centers)), int(centers.numel()), ptrs, int(wlist[1].numel()), nstreams, _p(sym),
+                                 _p(status), _p(ws), _stream()))
+    return sym

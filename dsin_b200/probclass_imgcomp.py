@@ -1,8 +1,9 @@
 """3-D masked-conv probability model (arch 'res_shallow') on libdsin_b200.
 
 Mirrors /root/reference/src/probclass_imgcomp.py: ``get_network_cls``, ``_Network3D.bitcost``
-(:63-106), ``auto_pad_value`` (:59-61), masks (:150-176).  The arithmetic-coding helpers
-(:361-482) are unused by the reference's main.py and are out of scope.
+(:63-106), ``auto_pad_value`` (:59-61), masks (:150-176).  The arithmetic-coding helpers (:361-482) have no
+caller in the reference; ``encode_symbols`` / ``decode_symbols`` below are the coder they were written for
+(PC1 format, csrc/pc_codec.cu, specified byte for byte in oracle/pc_codec.c).
 """
 from __future__ import annotations
 
@@ -11,7 +12,7 @@ import os
 import numpy as np
 import torch
 
-from . import ops, synth
+from . import bitstream, ops, synth
 
 
 # "tc3"/"tc1": the two 24->24 layers on tcgen05 (split fp16 / fp16); "simt": all CUDA cores
@@ -70,6 +71,17 @@ class _ResShallow(object):
                         torch.from_numpy(np.ascontiguousarray(b)).to(self.device)))
         self.weights = out
         self._tc = None
+        # live-tap-major fp32 slices for the entropy coder: (taps, cin, cout), taps in (kd, kh, kw) raster order
+        self._codec = []
+        for i, name in enumerate(("conv3d_conv0_mask", "res1/conv3d_conv1_mask", "res1/conv3d_conv2_mask",
+                                  "conv3d_conv2_mask")):
+            w = np.asarray(W[P + name + "/weights"], np.float32)
+            taps = [(0, kh, kw) for kh in range(3) for kw in range(3)] + [(1, 0, 0), (1, 0, 1), (1, 0, 2), (1, 1, 0)]
+            if i > 0:
+                taps.append((1, 1, 1))  # every layer but the first also sees the current position
+            packed = np.ascontiguousarray(np.stack([w[kd, kh, kw] for kd, kh, kw in taps]))
+            self._codec.append(torch.from_numpy(packed).to(self.device))
+            self._codec.append(torch.from_numpy(np.ascontiguousarray(W[P + name + "/biases"], np.float32)).to(self.device))
 
     def bitcost(self, q, target_symbols, is_training=False, pad_value=0):
         """q: qbar NCHW fp32, target_symbols NCHW int64 -> bits per symbol NCHW.  The fp64
@@ -89,3 +101,46 @@ class _ResShallow(object):
                                             float(pad_value), k=self.config.arch_param__k, L=self.L)
         bits._dsin_sum = sums
         return bits
+
+    # ------------------------------------------------------------------ real entropy coding (PC1)
+    def _check_codec(self):
+        if not self.config.use_centers_for_padding:
+            raise NotImplementedError("the PC1 coder pads with centres[0] (use_centers_for_padding = True)")
+        if self.config.arch_param__k != 24:
+            raise NotImplementedError("the PC1 coder is built for 24 hidden channels")
+
+    def encode_symbols(self, symbols, centers, nstreams=8):
+        """symbols (n,c,h,w) int64 CUDA, centers (L,) fp32 CUDA -> list of n self-describing bitstreams (bytes).
+        Each symbol is range-coded with the frequencies the context model predicts from the symbols before it
+        (src/probclass_imgcomp.py:421-470: get_freqs), so len(bitstream) is the real code length."""
+        self._check_codec()
+        n, c, hh, ww = symbols.shape
+        out, sizes, status = ops.pc_encode(symbols.contiguous(), centers, self._codec, nstreams)
+        sizes_h = sizes.cpu().numpy()
+        if int(status.item()) != 0:
+            raise RuntimeError("PC1 encoder: a stream exceeded its capacity")
+        out_h = out.cpu().numpy()
+        return [bitstream.pack([out_h[i, k, :sizes_h[i, k]].tobytes() for k in range(nstreams)], c, hh, ww, self.L)
+                for i in range(n)]
+
+    def decode_symbols(self, bitstreams, centers):
+        """list of n bitstreams (same shape) -> symbols (n,c,h,w) int64 CUDA."""
+        self._check_codec()
+        parsed = [bitstream.unpack(b) for b in bitstreams]
+        c, hh, ww, L, streams0 = parsed[0]
+        nstreams = len(streams0)
+        for pc, ph, pw, pL, st in parsed:
+            if (pc, ph, pw, pL, len(st)) != (c, hh, ww, L, nstreams):
+                raise ValueError("bitstreams of one batch must share their geometry")
+        if L != self.L:
+            raise ValueError("bitstream has {} centres, model has {}".format(L, self.L))
+        cap = max(max(len(s) for s in p[4]) for p in parsed) + 8
+        buf = np.zeros((len(parsed), nstreams, cap), np.uint8)
+        sizes = np.zeros((len(parsed), nstreams), np.int64)
+        for i, p in enumerate(parsed):
+            for k, s in enumerate(p[4]):
+                buf[i, k, :len(s)] = np.frombuffer(s, np.uint8)
+                sizes[i, k] = len(s)
+        dev = centers.device
+        return ops.pc_decode(torch.from_numpy(buf).to(dev), torch.from_numpy(sizes).to(dev), (len(parsed), c, hh, ww),
+                             centers, self._codec)

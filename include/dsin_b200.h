@@ -198,6 +198,24 @@ int64_t dsin_msssim_workspace_bytes(int groups, int batch, int height, int width
 int dsin_msssim(dsin_handle_t h, const float* img1, const float* img2, int groups, int batch, int height,
                 int width, int depth, double* out_g52, void* workspace, void* stream);
 
+/* ---- PC1 entropy coder: real bitstreams from the probability model --------------------------
+ * The reference has no coder, only its building blocks (src/probclass_imgcomp.py:361-482: per-symbol frequencies
+ * from the context model, causal order).  The byte-exact format is specified in oracle/pc_codec.c.
+ *   symbols   (n, c, hh, ww) int64, depth = bottleneck channel; ww <= 159
+ *   centers   L fp32 quantiser centres (device); weights: HOST array of 8 DEVICE pointers
+ *             {w0[13][K], b0[K], w1[14][K][K], b1, w2[14][K][K], b2, w3[14][K][L], b3[L]}, live-tap-major
+ *             (tap, cin, cout) slices of the masked (2,3,3) kernels (src/probclass_imgcomp.py:150-176,227-261), k = 24
+ *   bytes     (n, nstreams, cap) uint8, sizes (n, nstreams) int64: stream s of an image carries the depth slices
+ *             d == s (mod nstreams); *status (device int) becomes non-zero if a stream did not fit in cap bytes
+ * n * nstreams CTAs must be co-resident per launch (cooperative launch); larger batches are chunked internally. */
+int64_t dsin_pc_codec_workspace_bytes(int n, int c, int hh, int ww);
+int dsin_pc_encode(dsin_handle_t h, const int64_t* symbols, int n, int c, int hh, int ww, const float* centers, int L,
+                   const float* const* weights, int k, int nstreams, uint8_t* bytes, int64_t cap, int64_t* sizes,
+                   int* status, void* workspace, void* stream);
+int dsin_pc_decode(dsin_handle_t h, const uint8_t* bytes, int64_t cap, const int64_t* sizes, int n, int c, int hh, int ww,
+                   const float* centers, int L, const float* const* weights, int k, int nstreams, int64_t* symbols,
+                   int* status, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,3 +72,16 @@ def test_synthetic_pairs_are_seeded_and_uint8_valued():
     assert np.array_equal(x1, np.floor(x1)) and x1.min() >= 0 and x1.max() <= 255
     xs, ys = synth.make_batch(3, 40, 48, seed=9)
     assert xs.shape == (3, 3, 40, 48) and ys.shape == xs.shape
+
+
+def test_bitstream_container_roundtrip():
+    from dsin_b200 import bitstream
+    streams = [b"", b"\x01\x02\x03", bytes(range(200)), b"\xff"]
+    blob = bitstream.pack(streams, 32, 40, 153, 6)
+    assert blob[:4] == b"DSPC" and len(blob) == 16 + 4 * 4 + sum(map(len, streams))
+    assert bitstream.unpack(blob) == (32, 40, 153, 6, streams)
+    assert bitstream.payload_bits(blob) == 8 * 204
+    import pytest as _pt
+    for bad in (blob[:10], blob[:-1], blob + b"\x00", b"DSPX" + blob[4:], blob[:4] + b"\x09" + blob[5:]):
+        with _pt.raises(ValueError):
+            bitstream.unpack(bad)

@@ -41,7 +41,7 @@ def test_range_coder_carries_and_skewed_tables():
     bad, stream = P.rc_selftest(tabs, sym)
     assert bad == 0
     ideal = -np.log2(tabs[np.arange(n), sym] / 65536.0).sum()
-    assert 8 * len(stream) <= ideal + 16 and 8 * len(stream) >= ideal - 8
+    assert ideal - 32 <= 8 * len(stream) <= ideal + 16
     # tables that keep `low` near a byte boundary: long 0xFF runs and carry propagation
     tabs2 = np.tile(np.array([[1, 65534, 1]], np.uint32), (5000, 1))
     for pattern in ([2] * 5000, [1] * 4999 + [2], ([2] * 40 + [0]) * 121 + [1] * 39):
@@ -59,7 +59,7 @@ def test_roundtrip_random_symbols(weights, shape, nstreams):
     assert len(streams) == nstreams
     assert np.array_equal(P.decode(streams, shape, weights), sym)
     total = 8 * sum(len(s) for s in streams)
-    assert ideal - 8 * nstreams <= total <= ideal + 16 * nstreams + 8
+    assert ideal - 32 * nstreams <= total <= ideal + 16 * nstreams + 8   # trailing zero bytes are not stored
     # streams of depth slices that do not exist stay empty
     for k in range(shape[0], nstreams):
         assert streams[k] == b""
@@ -74,8 +74,8 @@ def test_code_length_matches_model_cross_entropy_and_stream_split(weights):
     eight, ideal8 = P.encode(sym, weights, nstreams=8)
     assert ideal1 == ideal8                                     # the model does not depend on the stream split
     assert abs(ideal1 - ce_bits) / ce_bits < 2e-4               # frequency quantisation only
-    assert 0 <= 8 * len(one[0]) - ideal1 <= 16                  # one stream: at most two bytes of overhead
-    assert 0 <= 8 * sum(map(len, eight)) - ideal8 <= 16 * 8
+    assert -32 <= 8 * len(one[0]) - ideal1 <= 16                # one stream: at most two bytes of overhead
+    assert -32 * 8 <= 8 * sum(map(len, eight)) - ideal8 <= 16 * 8
     assert np.array_equal(P.decode(one, sym.shape, weights), sym)
     assert np.array_equal(P.decode(eight, sym.shape, weights), sym)
     # a damaged stream decodes to different symbols from the damaged point of that stream on, never crashes
