@@ -400,6 +400,64 @@ def run_sif_only(args, rank, world, local_rank):
     }), flush=True)
 
 
+def run_codec(args, rank, world, local_rank):
+    """PC1 entropy coder (range coder driven by the probability model) on the symbols of one batch."""
+    import torch
+    import __graft_entry__ as g
+    torch.cuda.set_device(local_rank)
+    g.build()
+    from dsin_b200 import ops, synth
+    B = args.batch
+    ae = build_ae(local_rank)
+    pc = ae.pc_imgcomp
+    centers = ae.ae_imgcomp._centers
+    x, y = synth.make_batch(B, H, W, seed=1000)
+    out = ae.reconstruct_device(torch.tensor(x).cuda(), torch.tensor(y).cuda())
+    sym, est_bits = out["symbols"], float(out["bits_sum"].sum())
+    ns = args.streams
+    for _ in range(args.warmup):
+        b, sizes, _st = ops.pc_encode(sym, centers, pc._codec, ns)
+        ops.pc_decode(b, sizes, tuple(sym.shape), centers, pc._codec)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ops.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    enc_ms = dec_ms = 0.0
+    for _ in range(args.steps):
+        ev[0].record()
+        b, sizes, _st = ops.pc_encode(sym, centers, pc._codec, ns)
+        ev[1].record()
+        back = ops.pc_decode(b, sizes, tuple(sym.shape), centers, pc._codec)
+        ev[2].record()
+        torch.cuda.synchronize()
+        enc_ms += ev[0].elapsed_time(ev[1])
+        dec_ms += ev[1].elapsed_time(ev[2])
+    clocks = sampler.stop()
+    if rank != 0:
+        return
+    real_bits = 8 * int(sizes.sum())
+    mpix = B * args.steps * H * W * 1e-6
+    nsym = sym.numel()
+    print(json.dumps({
+        "metric": METRIC + " -- PC1 entropy coder only", "value": mpix / ((enc_ms + dec_ms) * 1e-3), "unit": "Mpixels/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": (enc_ms + dec_ms) / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fixed fmaf order) + u32 range coder",
+        "data": "synthetic", "config": {"workload": "SURVEY 8f N3: encode + decode of the symbols of batch %d of 320x1224 "
+                                                    "(32x40x153 symbols per image), %d streams per image" % (B, ns),
+                                        "batch_per_gpu": B, "streams": ns},
+        "encode_ms": enc_ms / args.steps, "decode_ms": dec_ms / args.steps,
+        "encode_mpix_s": mpix / (enc_ms * 1e-3), "decode_mpix_s": mpix / (dec_ms * 1e-3),
+        "symbols_per_s_decode": nsym * args.steps / (dec_ms * 1e-3),
+        "gpu_launches": int(ops.launch_count() - l0), "clocks": clocks, "roundtrip_identical": bool(torch.equal(back, sym)),
+        "payload_bits": real_bits, "estimated_bits": est_bits, "real_over_estimate": real_bits / est_bits,
+        "bpp_real": real_bits / (B * H * W), "bpp_estimate": est_bits / (B * H * W),
+        "roofline": {"bound": "latency", "note": "sequential dependence: 4 layers + range coder per wavefront step; "
+                     "per step the fmaf chains read 8 B of shared memory per FMA (the measured limiter)",
+                     "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None},
+    }), flush=True)
+
+
 def ae_dtype():
     from dsin_b200 import autoencoder_imgcomp
     return getattr(autoencoder_imgcomp, "COMPUTE_DTYPE", "f32")
@@ -413,7 +471,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="full", choices=["full", "sif"],
+    ap.add_argument("--streams", type=int, default=8, help="range-coder streams per image (--workload codec)")
+    ap.add_argument("--workload", default="full", choices=["full", "sif", "codec"],
                     help="full = BASELINE configs[1]; sif = configs[2] (SI-Finder in isolation, use --batch 32)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -426,6 +485,9 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.workload == "sif":
         run_sif_only(args, rank, world, local_rank)
+        return
+    if args.workload == "codec":
+        run_codec(args, rank, world, local_rank)
         return
     run_ours(args, rank, world, local_rank)
 

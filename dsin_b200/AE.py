@@ -314,6 +314,31 @@ class AE(object):
         self.last = out
         return dec_host[:B], tail[0].numpy(), dec_host[B:], tail[1].numpy(), bpp
 
+    # ------------------------------------------------------------------ real bitstreams
+    def compress(self, x, nstreams=8):
+        """x (B,3,H,W) uint8 / uint8-valued array -> list of B bitstreams (bytes).  Encoder + quantiser
+        (src/AE.py:50-53) followed by the PC1 range coder driven by the probability model
+        (the coder src/probclass_imgcomp.py:361-482 prepares for); 8 * len(bitstream) / (H * W) is the real bpp
+        that `bpp` of siNet_get_reconstructed estimates."""
+        xd = self._to_device(x, "x")
+        z = self._encode(xd, self.ae_imgcomp, is_training=False)
+        self.last = {"symbols": z.symbols, "qbar": z.qbar}
+        return self.pc_imgcomp.encode_symbols(z.symbols, self.ae_imgcomp._centers, nstreams=nstreams)
+
+    def decompress(self, bitstreams, y):
+        """Receiver: bitstreams of B images + the side images y (B,3,H,W) -> numpy (y_dec, y_syn, x_dec, x_with_si),
+        i.e. src/AE.py:132-148 without access to x.  The decoder input is qhard = centres[symbols]; the sender-side
+        graph feeds qbar = qsoft + (qhard - qsoft), which equals qhard up to one fp32 rounding."""
+        yd = self._to_device(y, "y")
+        sym = self.pc_imgcomp.decode_symbols(list(bitstreams), self.ae_imgcomp._centers)
+        if sym.shape[0] != yd.shape[0]:
+            raise ValueError("{} bitstreams for {} side images".format(sym.shape[0], yd.shape[0]))
+        qhard = self.ae_imgcomp._centers[sym]
+        out = self.decode_side_device(qhard.contiguous(), yd)
+        out["symbols"] = sym
+        self.last = out
+        return tuple(self._to_host([out[k] for k in ("y_dec", "y_syn", "x_dec", "x_with_si")]))
+
     def create_y_dec(self, y):
         yd = self._to_device(y, "y")
         z = self._encode(yd, self.ae_imgcomp, is_training=False)

@@ -90,6 +90,16 @@ def main(run_dict, args):
                 loss_list_saver(x_test, y_test, x_rec, y_syn, x_test.shape[0], str(model_name), bpp, root_save_img)
             results.append(float(bpp))
             print("  bpp = {:.5f}".format(bpp))
+            if args.real_bpp:  # entropy-code the symbols for real (probclass_imgcomp.py:361: "--real_bpp")
+                streams = ae.compress(x_test)
+                real = 8.0 * sum(len(b) for b in streams) / (x_test.shape[0] * x_test.shape[2] * x_test.shape[3])
+                print("  real bpp = {:.5f} ({} bytes incl. container)".format(real, sum(len(b) for b in streams)))
+                if args.save_dir is not None or run_dict["save_test_img"]:
+                    path = os.path.join(root_save_img, model_name)
+                    os.makedirs(path, exist_ok=True)
+                    for k, blob in enumerate(streams):
+                        with open(os.path.join(path, "{}_{}.dspc".format(i, k)), "wb") as f:
+                            f.write(blob)
     return results
 
 
@@ -109,6 +119,8 @@ def build_parser():
     parser.add_argument("--save_dir", type=str, default=None, help="image / list output root (default <cwd>/images/)")
     parser.add_argument("--no_save_test_img", action="store_true", help="reference default is to save (main.py:203)")
     parser.add_argument("--create_loss_list", action="store_true", help="append per-image metric lists (main.py:206)")
+    parser.add_argument("--real_bpp", action="store_true",
+                        help="also range-code the symbols (PC1 bitstream) and report / save the real size")
     return parser
 
 

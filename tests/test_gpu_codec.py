@@ -94,3 +94,26 @@ def test_container_and_error_paths():
     from dsin_b200 import ops
     with pytest.raises(RuntimeError, match="wider than 159"):   # wider than one CTA's step
         ops.pc_encode(torch.zeros((1, 2, 2, 160), dtype=torch.int64, device="cuda"), centers, pc._codec, 2)
+
+
+def test_compress_decompress_through_the_facade():
+    """Sender: AE.compress(x) -> bytes.  Receiver: AE.decompress(bytes, y) must reproduce what the one-call
+    path computes from x and y: identical symbols, hence identical SI-Finder matches; images equal up to the
+    qbar-vs-qhard rounding of the decoder input (documented in AE.decompress)."""
+    W = calibrated_weights(0)
+    ae = make_ae(80, 144, W)
+    x, y = synth.make_batch(2, 80, 144, seed=8)
+    x8, y8 = x.astype(np.uint8), y.astype(np.uint8)
+    y_dec, y_syn, x_dec, x_with_si, bpp = [np.array(a) for a in ae.siNet_get_reconstructed(x8, y8)]
+    sym_ref = ae.last["symbols"].clone()
+    blobs = ae.compress(x8)
+    assert all(isinstance(b, bytes) and b[:4] == b"DSPC" for b in blobs)
+    real_bpp = 8.0 * sum(bitstream.payload_bits(b) // 8 for b in blobs) / (2 * 80 * 144)
+    assert abs(real_bpp - float(bpp)) / float(bpp) < 0.03, (real_bpp, bpp)
+    r_y_dec, r_y_syn, r_x_dec, r_x_with_si = ae.decompress(blobs, y8)
+    assert torch.equal(ae.last["symbols"], sym_ref)
+    assert np.array_equal(r_y_dec, y_dec)                       # the side image path does not involve the bitstream
+    assert np.abs(r_x_dec - x_dec).max() < 2e-2                # qhard vs qbar: one fp32 rounding at the decoder input
+    assert np.abs(r_x_with_si - x_with_si).max() < 0.5          # (0..255 scale; patch matches may move on near-ties)
+    with pytest.raises(ValueError):
+        ae.decompress(blobs[:1], y8)
