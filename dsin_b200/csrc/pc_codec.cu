@@ -16,17 +16,19 @@
 //
 // Determinism.  Every activation is an fmaf chain in the order of oracle/pc_codec.c (bias; live taps in raster
 // order; input channels ascending); exp is a fixed polynomial; only correctly rounded IEEE operations are used.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "pc_codec_common.cuh"
 
 namespace {
 
+using namespace pc1;
+
 constexpr int K = 24;          // hidden channels
 constexpr int KP = 28;         // padded channel stride of the transposed weights in shared memory (conflict-free LDS.128)
-constexpr int MAXL = 8;        // centres
 constexpr int NT0 = 13, NT = 14;
 constexpr int MAXPOS = 33;
 constexpr int THREADS = 800;   // 33 positions x 24 channels = 792
-constexpr uint32_t TOTAL_BITS = 16, TOTAL = 1u << TOTAL_BITS;
 constexpr int PROGRESS_INIT = -1000000;
 
 __constant__ int c_taps[NT][3] = {{-1, -1, -1}, {-1, -1, 0}, {-1, -1, 1}, {-1, 0, -1}, {-1, 0, 0}, {-1, 0, 1}, {-1, 1, -1},
@@ -46,91 +48,6 @@ struct CodecArgs {
   int64_t cap;
   int64_t* sizes;  // [n][nstreams]
   int* status;     // != 0: a stream overflowed its capacity
-};
-
-__device__ __forceinline__ float relu(float x) { return x > 0.0f ? x : 0.0f; }
-
-__device__ __forceinline__ float exp_det(float x) {
-  if (x < -80.0f) x = -80.0f;
-  const float t = __fmul_rn(x, 1.4426950408889634f);
-  const float n = floorf(t);
-  const float f = __fsub_rn(t, n);
-  float p = 1.5353362e-4f;
-  p = __fmaf_rn(p, f, 1.3398874e-3f);
-  p = __fmaf_rn(p, f, 9.6184370e-3f);
-  p = __fmaf_rn(p, f, 5.5503324e-2f);
-  p = __fmaf_rn(p, f, 2.4022648e-1f);
-  p = __fmaf_rn(p, f, 6.9314720e-1f);
-  p = __fmaf_rn(p, f, 1.0f);
-  return __fmul_rn(p, __uint_as_float((uint32_t)((int)n + 127) << 23));
-}
-
-__device__ __forceinline__ void logits_to_freqs(const float* l, int L, uint32_t* f) {
-  float m = l[0];
-  int am = 0;
-  for (int i = 1; i < L; ++i)
-    if (l[i] > m) { m = l[i]; am = i; }
-  float e[MAXL], Z = 0.0f;
-  for (int i = 0; i < L; ++i) {
-    e[i] = exp_det(__fsub_rn(l[i], m));
-    Z = __fadd_rn(Z, e[i]);
-  }
-  const float scale = __fdiv_rn((float)(TOTAL - (uint32_t)L), Z);
-  uint32_t sum = 0;
-  for (int i = 0; i < L; ++i) {
-    f[i] = 1u + (uint32_t)__fmul_rn(e[i], scale);
-    sum += f[i];
-  }
-  f[am] += TOTAL - sum;
-}
-
-// ---------------------------------------------------------------- range coder (one thread per stream)
-struct RcEnc {
-  uint64_t low;
-  uint32_t range;
-  uint32_t cache;
-  uint64_t cache_size;
-  uint8_t* out;
-  int64_t pos, cap;
-  int overflow, skip_first;
-  __device__ void init(uint8_t* o, int64_t c) {
-    low = 0; range = 0xFFFFFFFFu; cache = 0; cache_size = 1; out = o; pos = 0; cap = c; overflow = 0; skip_first = 1;
-  }
-  __device__ void put(uint8_t b) {
-    if (skip_first) { skip_first = 0; return; }
-    if (pos < cap) out[pos] = b; else overflow = 1;
-    pos++;
-  }
-  __device__ void shift_low() {
-    if ((uint32_t)low < 0xFF000000u || (low >> 32) != 0) {
-      const uint8_t carry = (uint8_t)(low >> 32);
-      uint8_t c = (uint8_t)cache;
-      do {
-        put((uint8_t)(c + carry));
-        c = 0xFF;
-      } while (--cache_size != 0);
-      cache = (uint32_t)((low >> 24) & 0xFF);
-    }
-    cache_size++;
-    low = (low & 0x00FFFFFFull) << 8;
-  }
-  __device__ void encode(uint32_t cum, uint32_t freq) {
-    const uint32_t r = range >> TOTAL_BITS;
-    low += (uint64_t)r * cum;
-    range = r * freq;
-    while (range < (1u << 24)) { range <<= 8; shift_low(); }
-  }
-  __device__ void flush() {
-    const uint64_t hi = low + range - 1;
-    int k = 4;
-    uint64_t v = 0;
-    for (; k >= 0; --k) {
-      v = hi & ~((1ull << (8 * k)) - 1);
-      if (v >= low) break;
-    }
-    low = v;
-    for (int i = 0; i < 5 - k; ++i) shift_low();
-  }
 };
 
 constexpr int WIN = 128;  // bytes of the stream staged per step (a step consumes <= 2 bytes per symbol)
@@ -448,6 +365,52 @@ __global__ void pc_codec_prepare_kernel(CodecArgs p) {
   if (gid == 0 && p.reset_status) *p.status = 0;
 }
 
+// ---------------------------------------------------------------- fast encoder (all symbols known)
+__global__ void pc_qhard_kernel(const int64_t* __restrict__ sym, const float* __restrict__ centers, int L,
+                                float* __restrict__ q, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = sym[i];
+    q[i] = centers[s >= 0 && s < L ? s : 0];
+  }
+}
+
+// stage 2 of the fast encoder: one CTA per stream walks its depth slices in coding order (u = 5 h + w, then h);
+// all threads fetch the (cum, freq) words of UB wavefront steps into shared memory, one thread range-codes them.
+constexpr int UB = 32;
+__global__ void __launch_bounds__(256) pc_symbol_coder_kernel(const uint32_t* __restrict__ packed, int C, int H, int W,
+                                                              int nstreams, uint8_t* bytes, int64_t cap, int64_t* sizes,
+                                                              int* status) {
+  __shared__ uint32_t s_tab[UB * 32];
+  const int img = blockIdx.x / nstreams, stream = blockIdx.x % nstreams;
+  const uint32_t* tab = packed + (size_t)img * C * H * W;
+  RcEnc enc;
+  if (threadIdx.x == 0) enc.init(bytes + ((size_t)img * nstreams + stream) * cap, cap);
+  const int u_last = 5 * (H - 1) + (W - 1);
+  for (int d = stream; d < C; d += nstreams) {
+    for (int u0 = 0; u0 <= u_last; u0 += UB) {
+      for (int i = threadIdx.x; i < UB * 32; i += blockDim.x) {
+        const int u = u0 + i / 32;
+        int h_lo = u - (W - 1);
+        h_lo = h_lo > 0 ? (h_lo + 4) / 5 : 0;
+        const int h = h_lo + i % 32, w = u - 5 * h;
+        s_tab[i] = (u <= u_last && h < H && w >= 0 && w < W) ? tab[((size_t)d * H + h) * W + w] : 0u;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0)
+        for (int i = 0; i < UB * 32; ++i) {
+          const uint32_t e = s_tab[i];
+          if (e != 0u) enc.encode(e >> 16, e & 0xFFFFu);  // every frequency is >= 1, so 0 marks "no symbol here"
+        }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    enc.flush();
+    sizes[(size_t)img * nstreams + stream] = enc.pos;
+    if (enc.overflow) atomicExch(status, 1);
+  }
+}
+
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct Layout {
@@ -479,6 +442,25 @@ int run_codec(dsin_handle_t h, int decode, int64_t* symbols, int n, int c, int h
   DSIN_REQUIRE(h, L >= 2 && L <= MAXL, "2..8 centres");
   DSIN_REQUIRE(h, nstreams >= 1 && nstreams <= 64, "1..64 streams per image");
   DSIN_REQUIRE(h, (ww + 5) / 5 + 1 <= MAXPOS, "volume wider than 159 symbols (one CTA walks a slice 33 positions at a time)");
+  static const bool wavefront_encode = getenv("DSIN_PC_ENCODE_WAVEFRONT") != nullptr;
+  if (!decode && !wavefront_encode && L == 6 && (ww + 4) / 5 + 1 <= 32) {
+    // every symbol is known: frequency tables for the whole volume in parallel (probclass.cu), then one CTA per
+    // stream range-codes its symbols.  Same bytes as the wavefront kernel in encode mode.
+    const size_t nsym = (size_t)n * c * hh * ww;
+    uint8_t* ws = (uint8_t*)workspace;
+    float* qh = (float*)ws;
+    uint32_t* packed = (uint32_t*)(ws + align256(nsym * sizeof(float)));
+    void* tws = ws + 2 * align256(nsym * sizeof(float));
+    if (cudaMemsetAsync(status_out, 0, sizeof(int), st) != cudaSuccess)
+      return dsin_fail(h, DSIN_ERR_CUDA, "%s: memset failed", __func__);
+    pc_qhard_kernel<<<h->sm_count * 4, 256, 0, st>>>(symbols, centers, L, qh, (int64_t)nsym);
+    DSIN_LAUNCHED(h);
+    int rc = pc1_symbol_tables(h, qh, symbols, n, c, hh, ww, centers, L, wb, packed, tws, st);
+    if (rc != DSIN_OK) return rc;
+    pc_symbol_coder_kernel<<<n * nstreams, 256, 0, st>>>(packed, c, hh, ww, nstreams, bytes, cap, sizes, status_out);
+    DSIN_LAUNCHED(h);
+    return DSIN_OK;
+  }
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(pc_codec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
@@ -521,7 +503,10 @@ extern "C" {
 
 int64_t dsin_pc_codec_workspace_bytes(int n, int c, int hh, int ww) {
   if (n <= 0 || c <= 0 || hh <= 0 || ww <= 0) return -1;
-  return (int64_t)layout(n, c, hh, ww).total;
+  const int64_t wavefront = (int64_t)layout(n, c, hh, ww).total;
+  const int64_t fast = 2 * (int64_t)align256((size_t)n * c * hh * ww * sizeof(float)) +
+                       pc1_symbol_tables_workspace(n, c, hh, ww) + 256;
+  return wavefront > fast ? wavefront : fast;
 }
 
 int dsin_pc_encode(dsin_handle_t h, const int64_t* symbols, int n, int c, int hh, int ww, const float* centers, int L,

@@ -7,6 +7,7 @@
 // the last layer fuses ReLU + log-sum-exp cross entropy + log2(e) and the per-image fp64 sum.
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "pc_codec_common.cuh"
 
 struct PcP {
   const float* in;     // layer input (N,Di,Hi,Wi,CIN) or qbar_nchw for the first layer
@@ -20,15 +21,22 @@ struct PcP {
   int n, Di, Hi, Wi;   // input volume dims (for the first layer: padded dims)
   int c, hh, ww;       // bottleneck dims (first layer addressing)
   float pad_value;
+  const float* pad_ptr; // when set, the pad value is read from device memory (centres[0])
   unsigned live_mask;  // bit t set = tap t (d*9+h*3+w) has non-zero mask
   int relu;
+  int packed_taps;     // weights hold the live taps only, in tap order ([nlive][CIN][COUT])
+  uint32_t* packed;    // EXACT last layer: (cumulative frequency << 16 | frequency) of the symbol at each position
+  int L;
 };
 
-template <int CIN, int COUT, bool FIRST, bool LAST>
+// EXACT = the operation order of the PC1 entropy coder (oracle/pc_codec.c): acc = bias, then the fmaf chain over
+// live taps and input channels, ReLU as a compare-select; the last layer then emits the coder's frequencies.
+template <int CIN, int COUT, bool FIRST, bool LAST, bool EXACT = false>
 __global__ void __launch_bounds__(128) pc_conv3d_kernel(PcP p) {
-  extern __shared__ float s_w[];  // [18][CIN][COUT] + bias[COUT]
-  float* s_b = s_w + 18 * CIN * COUT;
-  for (int i = threadIdx.x; i < 18 * CIN * COUT; i += blockDim.x) s_w[i] = p.w[i];
+  extern __shared__ float s_w[];  // [18 or live][CIN][COUT] + bias[COUT]
+  const int ntaps_w = p.packed_taps ? __popc(p.live_mask) : 18;
+  float* s_b = s_w + ntaps_w * CIN * COUT;
+  for (int i = threadIdx.x; i < ntaps_w * CIN * COUT; i += blockDim.x) s_w[i] = p.w[i];
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_b[i] = p.b[i];
   __syncthreads();
 
@@ -47,25 +55,26 @@ __global__ void __launch_bounds__(128) pc_conv3d_kernel(PcP p) {
   }
   float acc[COUT];
 #pragma unroll
-  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+  for (int o = 0; o < COUT; ++o) acc[o] = EXACT ? s_b[o] : 0.f;
   if (active) {
 #pragma unroll
     for (int t = 0; t < 18; ++t) {
       if (!((p.live_mask >> t) & 1u)) continue;
+      const int tw = p.packed_taps ? __popc(p.live_mask & ((1u << t) - 1u)) : t;  // slot of tap t in the weights
       int dd = t / 9, dh = (t / 3) % 3, dw = t % 3;
       int id = dq + dd, ih = hq + dh, iw = wq + dw;
       if (FIRST) {
         // padded volume (C+4, H+8, W+8), value = qbar or pad_value
         int cc = id - 4, yy = ih - 4, xx = iw - 4;
-        float v = p.pad_value;
+        float v = p.pad_ptr ? __ldg(p.pad_ptr) : p.pad_value;
         if (cc >= 0 && yy >= 0 && yy < p.hh && xx >= 0 && xx < p.ww)
           v = __ldg(p.in + (((int64_t)img * p.c + cc) * p.hh + yy) * p.ww + xx);
-        const float* wt = s_w + t * COUT;
+        const float* wt = s_w + tw * COUT;
 #pragma unroll
         for (int o = 0; o < COUT; ++o) acc[o] = fmaf(v, wt[o], acc[o]);
       } else {
         const float* ip = p.in + ((((int64_t)img * p.Di + id) * p.Hi + ih) * p.Wi + iw) * CIN;
-        const float* wt = s_w + t * CIN * COUT;
+        const float* wt = s_w + tw * CIN * COUT;
 #pragma unroll 4
         for (int ci = 0; ci < CIN; ++ci) {
           float v = __ldg(ip + ci);
@@ -76,8 +85,8 @@ __global__ void __launch_bounds__(128) pc_conv3d_kernel(PcP p) {
     }
 #pragma unroll
     for (int o = 0; o < COUT; ++o) {
-      float v = __fadd_rn(acc[o], s_b[o]);
-      if (p.relu) v = fmaxf(v, 0.f);
+      float v = EXACT ? acc[o] : __fadd_rn(acc[o], s_b[o]);
+      if (p.relu) v = EXACT ? pc1::relu(v) : fmaxf(v, 0.f);
       acc[o] = v;
     }
     if (p.skip) {
@@ -92,6 +101,20 @@ __global__ void __launch_bounds__(128) pc_conv3d_kernel(PcP p) {
       float* op = p.out + idx * COUT;
 #pragma unroll
       for (int o = 0; o < COUT; ++o) op[o] = acc[o];
+    }
+  } else if (EXACT) {
+    if (active) {
+      uint32_t f[pc1::MAXL];
+      pc1::logits_to_freqs(acc, COUT, f);
+      const int64_t o_nchw = (((int64_t)img * Do + dq) * Ho + hq) * Wo + wq;
+      const int sy = (int)p.sym[o_nchw];
+      uint32_t cum = 0;
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) cum += o < sy ? f[o] : 0u;
+      uint32_t fs = f[0];
+#pragma unroll
+      for (int o = 1; o < COUT; ++o) fs = o == sy ? f[o] : fs;
+      p.packed[o_nchw] = cum << 16 | fs;  // cum <= 65535, 1 <= f <= 65531
     }
   } else {
     // softmax cross entropy with the target symbol, in bits
@@ -354,5 +377,48 @@ extern "C" int dsin_probclass_bits_tc(dsin_handle_t h, const float* qbar, const 
     pc_cross_entropy_kernel<<<dim3(blocks, n), 256, 0, st>>>(logits, symbols, bits_nchw, bits_sum, per_img, n);
     DSIN_LAUNCHED(h);
   }
+  return DSIN_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// PC1 fast encoder, stage 1: with every symbol known, the context model needs no sequential schedule -- run the
+// four layers over the whole volume (coder operation order) and keep only each symbol's own interval.
+// ---------------------------------------------------------------------------------------------
+int64_t pc1_symbol_tables_workspace(int n, int c, int hh, int ww) {
+  return dsin_probclass_workspace_bytes(n, c, hh, ww, 24);
+}
+
+int pc1_symbol_tables(dsin_handle_t h, const float* qhard_nchw, const int64_t* symbols, int n, int c, int hh, int ww,
+                      const float* centers, int L, const float* const* wb, uint32_t* packed, void* workspace,
+                      cudaStream_t st) {
+  DSIN_REQUIRE(h, L == 6, "the full-volume tables are built for 6 centres");
+  const int k = 24;
+  int64_t v0 = (int64_t)n * (c + 3) * (hh + 6) * (ww + 6);
+  int64_t v1 = (int64_t)n * (c + 2) * (hh + 4) * (ww + 4);
+  int64_t v2 = (int64_t)n * (c + 1) * (hh + 2) * (ww + 2);
+  int64_t v3 = (int64_t)n * c * hh * ww;
+  float* a0 = (float*)workspace;
+  float* a1 = a0 + v0 * k;
+  float* a2 = a1 + v1 * k;
+  const unsigned first = pc_live_mask(true), other = pc_live_mask(false);
+  PcP p;
+  memset(&p, 0, sizeof(p));
+  p.n = n; p.c = c; p.hh = hh; p.ww = ww; p.pad_ptr = centers; p.packed_taps = 1; p.L = L;  // pad = centres[0]
+  p.in = qhard_nchw; p.w = wb[0]; p.b = wb[1]; p.out = a0; p.Di = c + 4; p.Hi = hh + 8; p.Wi = ww + 8;
+  p.live_mask = first; p.relu = 1;
+  pc_conv3d_kernel<1, 24, true, false, true><<<(unsigned)((v0 + 127) / 128), 128, (13 * 24 + 24) * sizeof(float), st>>>(p);
+  DSIN_LAUNCHED(h);
+  const size_t smem24 = (14 * 24 * 24 + 24) * sizeof(float);
+  p.in = a0; p.w = wb[2]; p.b = wb[3]; p.out = a1; p.Di = c + 3; p.Hi = hh + 6; p.Wi = ww + 6; p.live_mask = other;
+  pc_conv3d_kernel<24, 24, false, false, true><<<(unsigned)((v1 + 127) / 128), 128, smem24, st>>>(p);
+  DSIN_LAUNCHED(h);
+  p.in = a1; p.w = wb[4]; p.b = wb[5]; p.out = a2; p.skip = a0; p.Di = c + 2; p.Hi = hh + 4; p.Wi = ww + 4; p.relu = 0;
+  pc_conv3d_kernel<24, 24, false, false, true><<<(unsigned)((v2 + 127) / 128), 128, smem24, st>>>(p);
+  DSIN_LAUNCHED(h);
+  p.in = a2; p.w = wb[6]; p.b = wb[7]; p.out = nullptr; p.skip = nullptr; p.Di = c + 1; p.Hi = hh + 2; p.Wi = ww + 2;
+  p.relu = 1; p.sym = symbols; p.packed = packed;
+  pc_conv3d_kernel<24, 6, false, true, true><<<(unsigned)((v3 + 127) / 128), 128, (14 * 24 * 6 + 6) * sizeof(float), st>>>(p);
+  DSIN_LAUNCHED(h);
   return DSIN_OK;
 }
