@@ -1,5 +1,5 @@
-"""Times one trunk layer (3x3 128->128, 16 images of 80x306) of the tcgen05 conv; run under DSIN_TC_DEBUG
-variants to attribute time to TMA / MMA / epilogue."""
+"""Times one trunk layer (3x3 128->128, 16 images of 80x306) of the tcgen05 conv with 0 / 2 residual inputs and
+3 / 1 MMA terms; DSIN_NO_CTA2=1 selects the one-CTA kernel instead of the CTA-pair kernel."""
 import os, sys
 sys.path.insert(0, ".")
 import numpy as np, torch
@@ -22,5 +22,5 @@ for terms in (3, 1):
             ops.conv_tc(x, tcl, res1=r if res else None, res2=r if res else None, terms=terms)
         e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 20 * 1e3
-        print("debug=%s terms=%d residuals=%d: %.1f us  (%.0f TFLOP/s algorithmic)" % (
-            os.environ.get("DSIN_TC_DEBUG", "0"), terms, 2 * res, us, 2.0 * n * hh * ww * 9 * 128 * 128 / us / 1e6))
+        print("cta_pairs=%s terms=%d residuals=%d: %.1f us  (%.0f TFLOP/s algorithmic)" % (
+            "DSIN_NO_CTA2" not in os.environ, terms, 2 * res, us, 2.0 * n * hh * ww * 9 * 128 * 128 / us / 1e6))
