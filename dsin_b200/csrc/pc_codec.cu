@@ -28,7 +28,7 @@ constexpr int K = 24;          // hidden channels
 constexpr int KP = 28;         // padded channel stride of the transposed weights in shared memory (conflict-free LDS.128)
 constexpr int NT0 = 13, NT = 14;
 constexpr int MAXPOS = 33;
-constexpr int THREADS = 800;   // 33 positions x 24 channels = 792
+constexpr int THREADS = 416;   // 33 positions x 12 channel pairs = 396 (13 warps: ~150 registers per thread)
 constexpr int PROGRESS_INIT = -1000000;
 
 __constant__ int c_taps[NT][3] = {{-1, -1, -1}, {-1, -1, 0}, {-1, -1, 1}, {-1, 0, -1}, {-1, 0, 0}, {-1, 0, 1}, {-1, 1, -1},
@@ -48,6 +48,7 @@ struct CodecArgs {
   int64_t cap;
   int64_t* sizes;  // [n][nstreams]
   int* status;     // != 0: a stream overflowed its capacity
+  long long* prof; // optional: per-phase cycle counters of one CTA (DSIN_PC_PROFILE)
 };
 
 constexpr int WIN = 128;  // bytes of the stream staged per step (a step consumes <= 2 bytes per symbol)
@@ -66,18 +67,6 @@ struct RcDec {
   __device__ void init(const uint8_t* i, int64_t l, const uint8_t* w) {
     in = i; pos = 0; len = l; range = 0xFFFFFFFFu; code = 0; win = w; wbase = -WIN;
     for (int k = 0; k < 4; ++k) code = (code << 8) | get();
-  }
-  __device__ int decode(const uint32_t* f, int L) {
-    const uint32_t r = range >> TOTAL_BITS;
-    uint32_t v = code / r;
-    if (v > TOTAL - 1) v = TOTAL - 1;
-    uint32_t cum = 0;
-    int s = 0;
-    while (s < L - 1 && cum + f[s] <= v) { cum += f[s]; ++s; }
-    code -= cum * r;
-    range = r * f[s];
-    while (range < (1u << 24)) { code = (code << 8) | get(); range <<= 8; }
-    return s;
   }
 };
 
@@ -127,7 +116,7 @@ __device__ __forceinline__ float dot24(float acc, const float* __restrict__ wt /
 // the same chain with the inputs of all 14 taps staged in shared memory ([NT][K] floats of this position)
 __device__ __forceinline__ float dot24_staged(float acc, const float* __restrict__ wt, int cout_stride,
                                               const float* __restrict__ xin) {
-#pragma unroll 2
+#pragma unroll
   for (int t = 0; t < NT; ++t) {
     const float4* w4 = reinterpret_cast<const float4*>(wt + (size_t)t * cout_stride);
     const float4* x4 = reinterpret_cast<const float4*>(xin + t * K);
@@ -142,6 +131,32 @@ __device__ __forceinline__ float dot24_staged(float acc, const float* __restrict
     }
   }
   return acc;
+}
+
+// two output channels of one position: the staged inputs are read once for both chains
+__device__ __forceinline__ void dot24_staged2(float& acc_a, float& acc_b, const float* __restrict__ wa,
+                                              const float* __restrict__ wb, int cout_stride,
+                                              const float* __restrict__ xin) {
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const float4* a4 = reinterpret_cast<const float4*>(wa + (size_t)t * cout_stride);
+    const float4* b4 = reinterpret_cast<const float4*>(wb + (size_t)t * cout_stride);
+    const float4* x4 = reinterpret_cast<const float4*>(xin + t * K);
+#pragma unroll
+    for (int g = 0; g < K / 4; ++g) {
+      const float4 xv = x4[g];
+      const float4 av = a4[g];
+      const float4 bv = b4[g];
+      acc_a = __fmaf_rn(xv.x, av.x, acc_a);
+      acc_b = __fmaf_rn(xv.x, bv.x, acc_b);
+      acc_a = __fmaf_rn(xv.y, av.y, acc_a);
+      acc_b = __fmaf_rn(xv.y, bv.y, acc_b);
+      acc_a = __fmaf_rn(xv.z, av.z, acc_a);
+      acc_b = __fmaf_rn(xv.z, bv.z, acc_b);
+      acc_a = __fmaf_rn(xv.w, av.w, acc_a);
+      acc_b = __fmaf_rn(xv.w, bv.w, acc_b);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(THREADS, 1) pc_codec_kernel(const CodecArgs p) {
@@ -225,10 +240,19 @@ __global__ void __launch_bounds__(THREADS, 1) pc_codec_kernel(const CodecArgs p)
   const uint8_t* my_stream = p.bytes + ((size_t)img * p.nstreams + stream) * p.cap;
   const int64_t my_len = p.decode ? p.sizes[(size_t)img * p.nstreams + stream] : 0;
 
-  const int j = tid / K, co = tid % K;     // (position, channel) of the 24-channel layers
+  const int j = tid / (K / 2), co = tid % (K / 2), cob = co + K / 2;  // position, the thread's two channels
   const int jl = tid / MAXL, il = tid % MAXL;  // (position, logit)
   const int u_min = 5 * -3 - 3, u_max = 5 * (H + 2) + (W + 2);
 
+  long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long pt = clock64();
+  const bool profiling = p.prof != nullptr && blockIdx.x == 1 % gridDim.x && tid == 0;
+#define PC_MARK(i)                      \
+  if (profiling) {                      \
+    const long long now = clock64();    \
+    pf[i] += now - pt;                  \
+    pt = now;                           \
+  }
   for (int d = stream; d < C; d += p.nstreams) {
     for (int u = u_min; u <= u_max; ++u) {
       // positions of this step: h in [h_lo, h_hi], w = u - 5 h in [-3, W+2]
@@ -241,24 +265,29 @@ __global__ void __launch_bounds__(THREADS, 1) pc_codec_kernel(const CodecArgs p)
       const int npos = h_hi - h_lo + 1;
       if (d > 0 && tid == 0) {  // slice d - 1 must be complete through step u + 6
         const int need = u + 6 < u_max ? u + 6 : u_max;
-        while (ld_acquire(progress + d - 1) < need) __nanosleep(64);
-        __threadfence();
+        while (ld_acquire(progress + d - 1) < need) __nanosleep(32);
       }
       __syncthreads();
+      // step u - 1 is complete (its writes precede the barrier): publish it from another warp, off the critical path
+      if (tid == 32 && u > u_min) st_release(progress + d, u - 1);
+      PC_MARK(0)
       const int h = h_lo + j, w = u - 5 * h;
       const bool act = j < npos;
       // ---- layer 0: 13 taps of q (1 channel)
       if (act) {
-        float acc = s_b0[co];
+        float acc = s_b0[co], accb = s_b0[cob];
 #pragma unroll
         for (int t = 0; t < NT0; ++t) {
           const int dd = d + c_taps[t][0];
           const float x = dd < 0 ? pad : __ldcg(q_at(dd, h + c_taps[t][1], w + c_taps[t][2]));
           acc = __fmaf_rn(x, s_w0[t * K + co], acc);
+          accb = __fmaf_rn(x, s_w0[t * K + cob], accb);
         }
         a0_at(d, h, w)[co] = relu(acc);
+        a0_at(d, h, w)[cob] = relu(accb);
       }
       __syncthreads();
+      PC_MARK(1)
       // One L2 round trip per layer: all threads gather the 14 x 24 inputs of every position of the step into
       // shared memory (constant vector for the padding-only slices d < 0), then each (position, channel)
       // thread runs its fmaf chain out of shared memory.
@@ -280,16 +309,26 @@ __global__ void __launch_bounds__(THREADS, 1) pc_codec_kernel(const CodecArgs p)
       // ---- layer 1
       gather(a0_at, s_k0, -2, H + 2, W + 2);
       __syncthreads();
-      if (act && h >= -2 && h < H + 2 && w >= -2 && w < W + 2)
-        a1_at(d, h, w)[co] = relu(dot24_staged(s_b1[co], s_w1 + co * KP, K * KP, s_in + j * NT * K));
+      PC_MARK(2)
+      if (act && h >= -2 && h < H + 2 && w >= -2 && w < W + 2) {
+        float ya = s_b1[co], yb = s_b1[cob];
+        dot24_staged2(ya, yb, s_w1 + co * KP, s_w1 + cob * KP, K * KP, s_in + j * NT * K);
+        a1_at(d, h, w)[co] = relu(ya);
+        a1_at(d, h, w)[cob] = relu(yb);
+      }
       __syncthreads();
+      PC_MARK(3)
       // ---- layer 2 (+ skip)
       gather(a1_at, s_k1, -1, H + 1, W + 1);
       __syncthreads();
-      if (act && h >= -1 && h < H + 1 && w >= -1 && w < W + 1)
-        a2_at(d, h, w)[co] = __fadd_rn(dot24_staged(s_b2[co], s_w2 + co * KP, K * KP, s_in + j * NT * K),
-                                       __ldcg(a0_at(d, h, w) + co));
+      if (act && h >= -1 && h < H + 1 && w >= -1 && w < W + 1) {
+        float ya = s_b2[co], yb = s_b2[cob];
+        dot24_staged2(ya, yb, s_w2 + co * KP, s_w2 + cob * KP, K * KP, s_in + j * NT * K);
+        a2_at(d, h, w)[co] = __fadd_rn(ya, __ldcg(a0_at(d, h, w) + co));
+        a2_at(d, h, w)[cob] = __fadd_rn(yb, __ldcg(a0_at(d, h, w) + cob));
+      }
       __syncthreads();
+      PC_MARK(4)
       // ---- logits
       gather(a2_at, s_k2, 0, H, W);
       __syncthreads();
@@ -299,11 +338,18 @@ __global__ void __launch_bounds__(THREADS, 1) pc_codec_kernel(const CodecArgs p)
           s_logit[jl * MAXL + il] = relu(dot24_staged(s_b3[il], s_w3 + il * KP, MAXL * KP, s_in + jl * NT * K));
       }
       __syncthreads();
+      PC_MARK(5)
       // ---- frequency tables, one thread per position; the coder's global reads are staged by other threads
       if (tid < npos) {
         const int hf = h_lo + tid, wf = u - 5 * hf;
         if (hf >= 0 && hf < H && wf >= 0 && wf < W) {
-          logits_to_freqs(s_logit + tid * MAXL, L, s_freq + tid * MAXL);
+          uint32_t f[MAXL];
+          logits_to_freqs(s_logit + tid * MAXL, L, f);
+          uint32_t c = 0;  // s_freq holds the cumulative table: entry i = sum of f[0..i-1]; the last is implied (65536)
+          for (int i = 0; i < L; ++i) {
+            s_freq[tid * MAXL + i] = c;
+            c += f[i];
+          }
           if (!p.decode) s_sym[tid] = (int)sym[((size_t)d * H + hf) * W + wf];
         }
       } else if (p.decode && tid >= 64 && tid < 64 + WIN) {
@@ -311,33 +357,55 @@ __global__ void __launch_bounds__(THREADS, 1) pc_codec_kernel(const CodecArgs p)
         s_win[tid - 64] = at < my_len ? my_stream[at] : 0;
       }
       __syncthreads();
-      // ---- range coder over the step's symbols (increasing h), publish the step
+      PC_MARK(6)
+      // ---- range coder over the step's symbols (increasing h).  Decoding is division-free: the symbol is the
+      // number of cumulative thresholds r * cum[i] that the code value has reached (floor(code / r) >= cum[i]).
       if (tid == 0) {
-        if (p.decode) dec.wbase = *s_pos;
+        uint32_t code = dec.code, range = dec.range;
+        int wofs = 0;                      // read offset into the staged window (s_win = stream[pos0 ...])
+        const int64_t pos0 = dec.pos;
         for (int jj = 0; jj < npos; ++jj) {
           const int hc = h_lo + jj, wc = u - 5 * hc;
           if (hc < 0 || hc >= H || wc < 0 || wc >= W) continue;
-          const uint32_t* f = s_freq + jj * MAXL;
-          int64_t* sp = sym + ((size_t)d * H + hc) * W + wc;
-          int s;
+          const uint32_t* cumt = s_freq + jj * MAXL;
           if (p.decode) {
-            s = dec.decode(f, L);
-            *sp = s;
-            *q_at(d, hc, wc) = s_cent[s];
+            const uint32_t r = range >> TOTAL_BITS;
+            uint32_t lo = 0;
+            int sy = 0;
+#pragma unroll
+            for (int i = 1; i < MAXL; ++i)  // thresholds ascend: the last one reached is the symbol
+              if (i < L) {
+                const uint32_t ci = cumt[i];
+                if (code >= r * ci) { sy = i; lo = ci; }  // r < 2^16 and ci < 2^16: the product fits 32 bits
+              }
+            const uint32_t hi = sy + 1 < L ? cumt[sy + 1] : TOTAL;
+            code -= lo * r;
+            range = r * (hi - lo);
+            while (range < (1u << 24)) {
+              const int64_t at = pos0 + wofs;
+              const uint32_t byte = wofs < WIN ? s_win[wofs] : (at < my_len ? my_stream[at] : 0);
+              ++wofs;
+              code = (code << 8) | byte;
+              range <<= 8;
+            }
+            sym[((size_t)d * H + hc) * W + wc] = sy;
+            *q_at(d, hc, wc) = s_cent[sy];
           } else {
-            s = s_sym[jj];
-            uint32_t cum = 0;
-            for (int i = 0; i < s; ++i) cum += f[i];
-            enc.encode(cum, f[s]);
+            const int sy = s_sym[jj];
+            const uint32_t lo = cumt[sy], hi = sy + 1 < L ? cumt[sy + 1] : TOTAL;
+            enc.encode(lo, hi - lo);
           }
         }
-        if (p.decode) *s_pos = dec.pos;
-        __threadfence();
-        st_release(progress + d, u);
+        if (p.decode) { dec.code = code; dec.range = range; dec.pos = pos0 + wofs; *s_pos = dec.pos; }
       }
+      PC_MARK(7)
       // the barrier at the top of the next step orders the coder's q writes before the next layer-0 reads
     }
+    __syncthreads();
+    if (tid == 32) st_release(progress + d, u_max);
   }
+  if (profiling)
+    for (int i = 0; i < 8; ++i) p.prof[i] = pf[i];
   if (tid == 0 && !p.decode) {
     enc.flush();
     p.sizes[(size_t)img * p.nstreams + stream] = enc.pos;
@@ -488,11 +556,23 @@ int run_codec(dsin_handle_t h, int decode, int64_t* symbols, int n, int c, int h
     a.bytes = bytes + (size_t)i0 * nstreams * cap; a.cap = cap; a.sizes = sizes + (size_t)i0 * nstreams;
     pc_codec_prepare_kernel<<<h->sm_count * 4, 256, 0, st>>>(a);
     DSIN_LAUNCHED(h);
+    static const bool want_prof = getenv("DSIN_PC_PROFILE") != nullptr;
+    long long* prof = nullptr;
+    if (want_prof && cudaMallocManaged(&prof, 8 * sizeof(long long)) == cudaSuccess) {
+      memset(prof, 0, 8 * sizeof(long long));
+      a.prof = prof;
+    }
     void* params[] = {&a};
     if (cudaLaunchCooperativeKernel((const void*)pc_codec_kernel, dim3(ni * nstreams), dim3(THREADS), params, kSmemBytes,
                                     st) != cudaSuccess)
       return dsin_fail(h, DSIN_ERR_CUDA, "%s: cooperative launch failed (are all CTAs co-resident?)", __func__);
     DSIN_LAUNCHED(h);
+    if (prof) {  // debugging aid only: synchronises
+      cudaStreamSynchronize(st);
+      fprintf(stderr, "pc_codec phases (cycles of one CTA): wait %lld | L0 %lld | gather1 %lld | L1 %lld | L2 %lld | logits %lld | "
+                      "freq %lld | coder %lld\n", prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], prof[6], prof[7]);
+      cudaFree(prof);
+    }
   }
   return DSIN_OK;
 }
