@@ -28,7 +28,9 @@ constexpr int K = 24;          // hidden channels
 constexpr int KP = 28;         // padded channel stride of the transposed weights in shared memory (conflict-free LDS.128)
 constexpr int NT0 = 13, NT = 14;
 constexpr int MAXPOS = 33;
-constexpr int THREADS = 416;   // 33 positions x 12 channel pairs = 396 (13 warps: ~150 registers per thread)
+constexpr int BULK = 288;      // nine bulk warps: 33 positions x 8 channel triples = 264 working threads
+constexpr int THREADS = 320;   // + the coder warp
+constexpr int MAXH = 64;       // rows (with halo) of the shared-memory rings: symbol rows <= 58
 constexpr int PROGRESS_INIT = -1000000;
 
 __constant__ int c_taps[NT][3] = {{-1, -1, -1}, {-1, -1, 0}, {-1, -1, 1}, {-1, 0, -1}, {-1, 0, 0}, {-1, 0, 1}, {-1, 1, -1},
@@ -48,27 +50,9 @@ struct CodecArgs {
   int64_t cap;
   int64_t* sizes;  // [n][nstreams]
   int* status;     // != 0: a stream overflowed its capacity
-  long long* prof; // optional: per-phase cycle counters of one CTA (DSIN_PC_PROFILE)
 };
 
 constexpr int WIN = 128;  // bytes of the stream staged per step (a step consumes <= 2 bytes per symbol)
-struct RcDec {
-  uint32_t code, range;
-  const uint8_t* in;
-  int64_t pos, len;
-  const uint8_t* win;   // shared-memory copy of in[wbase, wbase + WIN)
-  int64_t wbase;
-  __device__ uint8_t get() {
-    const int64_t o = pos - wbase;
-    const uint8_t b = pos >= len ? 0 : (o >= 0 && o < WIN ? win[o] : in[pos]);
-    pos++;
-    return b;
-  }
-  __device__ void init(const uint8_t* i, int64_t l, const uint8_t* w) {
-    in = i; pos = 0; len = l; range = 0xFFFFFFFFu; code = 0; win = w; wbase = -WIN;
-    for (int k = 0; k < 4; ++k) code = (code << 8) | get();
-  }
-};
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -79,86 +63,35 @@ __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// one output channel of a 24-input layer at one position: bias, then 14 taps x 24 channels in order.
-// src(t) returns the 24 input channels of tap t (global, L2-coherent loads) or nullptr for the constant vector.
-template <typename Src>
-__device__ __forceinline__ float dot24(float acc, const float* __restrict__ wt /* [NT][cout][KP], this co */, int cout_stride,
-                                       const float* __restrict__ kconst, Src src) {
-#pragma unroll 1
-  for (int t = 0; t < NT; ++t) {
-    const float* x = src(t);
-    const float4* w4 = reinterpret_cast<const float4*>(wt + (size_t)t * cout_stride);
-    if (x != nullptr) {
-      const float4* x4 = reinterpret_cast<const float4*>(x);
+// NC fmaf chains (output channels) of one position advanced over one tap: x = the 24 input channels of the tap
+// (shared memory), w0 = the tap's weights of chain 0 ([KP] floats), the other chains follow at chain_stride floats.
+// Within a chain the order is the coder's: input channels ascending.
+template <int NC>
+__device__ __forceinline__ void chain_tap(float (&acc)[NC], const float* __restrict__ w0, int chain_stride,
+                                          const float* __restrict__ x) {
+  const float4* x4 = reinterpret_cast<const float4*>(x);
 #pragma unroll
-      for (int g = 0; g < K / 4; ++g) {
-        const float4 xv = __ldcg(x4 + g);
-        const float4 wv = w4[g];
-        acc = __fmaf_rn(xv.x, wv.x, acc);
-        acc = __fmaf_rn(xv.y, wv.y, acc);
-        acc = __fmaf_rn(xv.z, wv.z, acc);
-        acc = __fmaf_rn(xv.w, wv.w, acc);
-      }
-    } else {
+  for (int g = 0; g < K / 4; ++g) {
+    const float4 xv = x4[g];
 #pragma unroll
-      for (int g = 0; g < K / 4; ++g) {
-        const float4 wv = w4[g];
-        acc = __fmaf_rn(kconst[4 * g + 0], wv.x, acc);
-        acc = __fmaf_rn(kconst[4 * g + 1], wv.y, acc);
-        acc = __fmaf_rn(kconst[4 * g + 2], wv.z, acc);
-        acc = __fmaf_rn(kconst[4 * g + 3], wv.w, acc);
-      }
-    }
-  }
-  return acc;
-}
-
-// the same chain with the inputs of all 14 taps staged in shared memory ([NT][K] floats of this position)
-__device__ __forceinline__ float dot24_staged(float acc, const float* __restrict__ wt, int cout_stride,
-                                              const float* __restrict__ xin) {
-#pragma unroll
-  for (int t = 0; t < NT; ++t) {
-    const float4* w4 = reinterpret_cast<const float4*>(wt + (size_t)t * cout_stride);
-    const float4* x4 = reinterpret_cast<const float4*>(xin + t * K);
-#pragma unroll
-    for (int g = 0; g < K / 4; ++g) {
-      const float4 xv = x4[g];
-      const float4 wv = w4[g];
-      acc = __fmaf_rn(xv.x, wv.x, acc);
-      acc = __fmaf_rn(xv.y, wv.y, acc);
-      acc = __fmaf_rn(xv.z, wv.z, acc);
-      acc = __fmaf_rn(xv.w, wv.w, acc);
-    }
-  }
-  return acc;
-}
-
-// two output channels of one position: the staged inputs are read once for both chains
-__device__ __forceinline__ void dot24_staged2(float& acc_a, float& acc_b, const float* __restrict__ wa,
-                                              const float* __restrict__ wb, int cout_stride,
-                                              const float* __restrict__ xin) {
-#pragma unroll
-  for (int t = 0; t < NT; ++t) {
-    const float4* a4 = reinterpret_cast<const float4*>(wa + (size_t)t * cout_stride);
-    const float4* b4 = reinterpret_cast<const float4*>(wb + (size_t)t * cout_stride);
-    const float4* x4 = reinterpret_cast<const float4*>(xin + t * K);
-#pragma unroll
-    for (int g = 0; g < K / 4; ++g) {
-      const float4 xv = x4[g];
-      const float4 av = a4[g];
-      const float4 bv = b4[g];
-      acc_a = __fmaf_rn(xv.x, av.x, acc_a);
-      acc_b = __fmaf_rn(xv.x, bv.x, acc_b);
-      acc_a = __fmaf_rn(xv.y, av.y, acc_a);
-      acc_b = __fmaf_rn(xv.y, bv.y, acc_b);
-      acc_a = __fmaf_rn(xv.z, av.z, acc_a);
-      acc_b = __fmaf_rn(xv.z, bv.z, acc_b);
-      acc_a = __fmaf_rn(xv.w, av.w, acc_a);
-      acc_b = __fmaf_rn(xv.w, bv.w, acc_b);
+    for (int c = 0; c < NC; ++c) {
+      const float4 wv = reinterpret_cast<const float4*>(w0 + c * chain_stride)[g];
+      acc[c] = __fmaf_rn(xv.x, wv.x, acc[c]);
+      acc[c] = __fmaf_rn(xv.y, wv.y, acc[c]);
+      acc[c] = __fmaf_rn(xv.z, wv.z, acc[c]);
+      acc[c] = __fmaf_rn(xv.w, wv.w, acc[c]);
     }
   }
 }
 
+__device__ __forceinline__ void bar_bulk() { asm volatile("bar.sync 1, %0;" ::"n"(BULK) : "memory"); }
+
+// Software pipeline of one CTA (one stream).  Taps 0..11 of every layer only need data that is at least three
+// steps old (previous slice, row h-1); only tap 12 (the left neighbour, previous step) and tap 13 (the position
+// itself, this step) are on the critical path -- and the coder's chain order ends with exactly those two.  So while
+// the coder warp range-codes step u, the nine bulk warps already accumulate taps 0..11 of step u+1 for all four
+// layers (partial chains stay in registers); after the barrier they finish the chains with taps 12/13 out of
+// shared-memory rings, layer by layer, and build the frequency tables of step u+1.
 __global__ void __launch_bounds__(THREADS, 1) pc_codec_kernel(const CodecArgs p) {
   extern __shared__ __align__(16) float smem[];
   float* s_w1 = smem;                       // [NT][K][KP]   transposed: (tap, co, ci)
@@ -174,9 +107,13 @@ __global__ void __launch_bounds__(THREADS, 1) pc_codec_kernel(const CodecArgs p)
   float* s_k2 = s_k1 + K;
   float* s_cent = s_k2 + K;                 // [MAXL]
   float* s_logit = s_cent + MAXL;           // [MAXPOS][MAXL]
-  uint32_t* s_freq = reinterpret_cast<uint32_t*>(s_logit + MAXPOS * MAXL);  // [MAXPOS][MAXL]
-  float* s_in = reinterpret_cast<float*>(s_freq + MAXPOS * MAXL);           // [MAXPOS][NT][K] staged layer inputs
-  int* s_sym = reinterpret_cast<int*>(s_in + MAXPOS * NT * K);              // [MAXPOS] symbols of the step (encode)
+  uint32_t* s_freq = reinterpret_cast<uint32_t*>(s_logit + MAXPOS * MAXL);  // [MAXPOS][MAXL] cumulative tables
+  float* s_in = reinterpret_cast<float*>(s_freq + MAXPOS * MAXL);           // [MAXPOS][NT][K] staged old taps
+  float* s_c0 = s_in + MAXPOS * NT * K;     // [2][MAXH][K] layer-0 values of the last two steps, by row
+  float* s_c1 = s_c0 + 2 * MAXH * K;
+  float* s_c2 = s_c1 + 2 * MAXH * K;
+  float* s_qc = s_c2 + 2 * MAXH * K;        // [MAXH] centre value decoded in the last step, by row
+  int* s_sym = reinterpret_cast<int*>(s_qc + MAXH);                         // [MAXPOS] symbols of the step (encode)
   long long* s_pos = reinterpret_cast<long long*>(s_sym + MAXPOS + 1);      // decoder read position (8-byte aligned)
   uint8_t* s_win = reinterpret_cast<uint8_t*>(s_pos + 1);                   // [WIN] stream bytes of the step (decode)
 
@@ -199,16 +136,24 @@ __global__ void __launch_bounds__(THREADS, 1) pc_codec_kernel(const CodecArgs p)
   if (tid < K) { s_b0[tid] = p.b0[tid]; s_b1[tid] = p.b1[tid]; s_b2[tid] = p.b2[tid]; }
   if (tid < MAXL) { s_b3[tid] = tid < L ? p.b3[tid] : 0.f; s_cent[tid] = tid < L ? p.centers[tid] : 0.f; }
   __syncthreads();
+  // activations of the padding-only slices d < 0 are position independent: three constant vectors
   if (tid < K) {
     float acc = s_b0[tid];
     for (int t = 0; t < NT0; ++t) acc = __fmaf_rn(pad, s_w0[t * K + tid], acc);
     s_k0[tid] = relu(acc);
   }
   __syncthreads();
-  if (tid < K) s_k1[tid] = relu(dot24(s_b1[tid], s_w1 + tid * KP, K * KP, s_k0, [](int) { return (const float*)nullptr; }));
+  if (tid < K) {
+    float acc[1] = {s_b1[tid]};
+    for (int t = 0; t < NT; ++t) chain_tap<1>(acc, s_w1 + (t * K + tid) * KP, 0, s_k0);
+    s_k1[tid] = relu(acc[0]);
+  }
   __syncthreads();
-  if (tid < K)
-    s_k2[tid] = __fadd_rn(dot24(s_b2[tid], s_w2 + tid * KP, K * KP, s_k1, [](int) { return (const float*)nullptr; }), s_k0[tid]);
+  if (tid < K) {
+    float acc[1] = {s_b2[tid]};
+    for (int t = 0; t < NT; ++t) chain_tap<1>(acc, s_w2 + (t * K + tid) * KP, 0, s_k1);
+    s_k2[tid] = __fadd_rn(acc[0], s_k0[tid]);
+  }
   __syncthreads();
 
   // ---- volumes of this image
@@ -226,187 +171,242 @@ __global__ void __launch_bounds__(THREADS, 1) pc_codec_kernel(const CodecArgs p)
   auto a1_at = [&](int d, int h, int w) { return a1 + (size_t)d * a1_plane + ((size_t)(h + 2) * (W + 4) + (w + 2)) * K; };
   auto a2_at = [&](int d, int h, int w) { return a2 + (size_t)d * a2_plane + ((size_t)(h + 1) * (W + 2) + (w + 1)) * K; };
 
-  RcEnc enc;
-  RcDec dec;
-  if (tid == 0) {
-    uint8_t* base = p.bytes + ((size_t)img * p.nstreams + stream) * p.cap;
-    if (p.decode) {
-      dec.init(base, p.sizes[(size_t)img * p.nstreams + stream], s_win);
-      *s_pos = dec.pos;
-    } else {
-      enc.init(base, p.cap);
-    }
-  }
   const uint8_t* my_stream = p.bytes + ((size_t)img * p.nstreams + stream) * p.cap;
   const int64_t my_len = p.decode ? p.sizes[(size_t)img * p.nstreams + stream] : 0;
-
-  const int j = tid / (K / 2), co = tid % (K / 2), cob = co + K / 2;  // position, the thread's two channels
-  const int jl = tid / MAXL, il = tid % MAXL;  // (position, logit)
-  const int u_min = 5 * -3 - 3, u_max = 5 * (H + 2) + (W + 2);
-
-  long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  long long pt = clock64();
-  const bool profiling = p.prof != nullptr && blockIdx.x == 1 % gridDim.x && tid == 0;
-#define PC_MARK(i)                      \
-  if (profiling) {                      \
-    const long long now = clock64();    \
-    pf[i] += now - pt;                  \
-    pt = now;                           \
-  }
-  for (int d = stream; d < C; d += p.nstreams) {
-    for (int u = u_min; u <= u_max; ++u) {
-      // positions of this step: h in [h_lo, h_hi], w = u - 5 h in [-3, W+2]
-      int h_lo = u - (W + 2);
-      h_lo = h_lo > 0 ? (h_lo + 4) / 5 : -((-h_lo) / 5);  // ceil(h_lo / 5)
-      if (h_lo < -3) h_lo = -3;
-      int h_hi = u + 3;
-      h_hi = h_hi >= 0 ? h_hi / 5 : -((-h_hi + 4) / 5);   // floor((u + 3) / 5)
-      if (h_hi > H + 2) h_hi = H + 2;
-      const int npos = h_hi - h_lo + 1;
-      if (d > 0 && tid == 0) {  // slice d - 1 must be complete through step u + 6
-        const int need = u + 6 < u_max ? u + 6 : u_max;
-        while (ld_acquire(progress + d - 1) < need) __nanosleep(32);
+  RcEnc enc;
+  uint32_t dec_code = 0, dec_range = 0xFFFFFFFFu;
+  int64_t dec_pos = 0;
+  if (tid == BULK) {
+    if (p.decode) {
+      for (int k = 0; k < 4; ++k) {
+        dec_code = (dec_code << 8) | (dec_pos < my_len ? my_stream[dec_pos] : 0);
+        ++dec_pos;
       }
-      __syncthreads();
-      // step u - 1 is complete (its writes precede the barrier): publish it from another warp, off the critical path
-      if (tid == 32 && u > u_min) st_release(progress + d, u - 1);
-      PC_MARK(0)
-      const int h = h_lo + j, w = u - 5 * h;
-      const bool act = j < npos;
-      // ---- layer 0: 13 taps of q (1 channel)
-      if (act) {
-        float acc = s_b0[co], accb = s_b0[cob];
-#pragma unroll
-        for (int t = 0; t < NT0; ++t) {
-          const int dd = d + c_taps[t][0];
-          const float x = dd < 0 ? pad : __ldcg(q_at(dd, h + c_taps[t][1], w + c_taps[t][2]));
-          acc = __fmaf_rn(x, s_w0[t * K + co], acc);
-          accb = __fmaf_rn(x, s_w0[t * K + cob], accb);
-        }
-        a0_at(d, h, w)[co] = relu(acc);
-        a0_at(d, h, w)[cob] = relu(accb);
-      }
-      __syncthreads();
-      PC_MARK(1)
-      // One L2 round trip per layer: all threads gather the 14 x 24 inputs of every position of the step into
-      // shared memory (constant vector for the padding-only slices d < 0), then each (position, channel)
-      // thread runs its fmaf chain out of shared memory.
-      auto gather = [&](auto at_fn, const float* kconst, int lo, int hiH, int hiW) {
-        const float4* k4 = reinterpret_cast<const float4*>(kconst);
-        float4* dst = reinterpret_cast<float4*>(s_in);
-        for (int idx = tid; idx < npos * NT * (K / 4); idx += THREADS) {
-          const int jj = idx / (NT * (K / 4)), r = idx % (NT * (K / 4));
-          const int t = r / (K / 4), g = r % (K / 4);
-          const int hh = h_lo + jj, ww = u - 5 * hh;
-          if (hh < lo || hh >= hiH || ww < lo || ww >= hiW) continue;
-          // tap offsets computed, not looked up: a thread-varying index into constant memory would serialise
-          const int dd = t < 9 ? d - 1 : d;
-          const int dh = t < 9 ? t / 3 - 1 : (t < 12 ? -1 : 0);
-          const int dw = t < 9 ? t % 3 - 1 : (t < 12 ? t - 10 : t - 13);
-          dst[idx] = dd < 0 ? k4[g] : __ldcg(reinterpret_cast<const float4*>(at_fn(dd, hh + dh, ww + dw)) + g);
-        }
-      };
-      // ---- layer 1
-      gather(a0_at, s_k0, -2, H + 2, W + 2);
-      __syncthreads();
-      PC_MARK(2)
-      if (act && h >= -2 && h < H + 2 && w >= -2 && w < W + 2) {
-        float ya = s_b1[co], yb = s_b1[cob];
-        dot24_staged2(ya, yb, s_w1 + co * KP, s_w1 + cob * KP, K * KP, s_in + j * NT * K);
-        a1_at(d, h, w)[co] = relu(ya);
-        a1_at(d, h, w)[cob] = relu(yb);
-      }
-      __syncthreads();
-      PC_MARK(3)
-      // ---- layer 2 (+ skip)
-      gather(a1_at, s_k1, -1, H + 1, W + 1);
-      __syncthreads();
-      if (act && h >= -1 && h < H + 1 && w >= -1 && w < W + 1) {
-        float ya = s_b2[co], yb = s_b2[cob];
-        dot24_staged2(ya, yb, s_w2 + co * KP, s_w2 + cob * KP, K * KP, s_in + j * NT * K);
-        a2_at(d, h, w)[co] = __fadd_rn(ya, __ldcg(a0_at(d, h, w) + co));
-        a2_at(d, h, w)[cob] = __fadd_rn(yb, __ldcg(a0_at(d, h, w) + cob));
-      }
-      __syncthreads();
-      PC_MARK(4)
-      // ---- logits
-      gather(a2_at, s_k2, 0, H, W);
-      __syncthreads();
-      {
-        const int hl = h_lo + jl, wl = u - 5 * hl;
-        if (jl < npos && il < L && hl >= 0 && hl < H && wl >= 0 && wl < W)
-          s_logit[jl * MAXL + il] = relu(dot24_staged(s_b3[il], s_w3 + il * KP, MAXL * KP, s_in + jl * NT * K));
-      }
-      __syncthreads();
-      PC_MARK(5)
-      // ---- frequency tables, one thread per position; the coder's global reads are staged by other threads
-      if (tid < npos) {
-        const int hf = h_lo + tid, wf = u - 5 * hf;
-        if (hf >= 0 && hf < H && wf >= 0 && wf < W) {
-          uint32_t f[MAXL];
-          logits_to_freqs(s_logit + tid * MAXL, L, f);
-          uint32_t c = 0;  // s_freq holds the cumulative table: entry i = sum of f[0..i-1]; the last is implied (65536)
-          for (int i = 0; i < L; ++i) {
-            s_freq[tid * MAXL + i] = c;
-            c += f[i];
-          }
-          if (!p.decode) s_sym[tid] = (int)sym[((size_t)d * H + hf) * W + wf];
-        }
-      } else if (p.decode && tid >= 64 && tid < 64 + WIN) {
-        const int64_t at = (int64_t)*s_pos + (tid - 64);
-        s_win[tid - 64] = at < my_len ? my_stream[at] : 0;
-      }
-      __syncthreads();
-      PC_MARK(6)
-      // ---- range coder over the step's symbols (increasing h).  Decoding is division-free: the symbol is the
-      // number of cumulative thresholds r * cum[i] that the code value has reached (floor(code / r) >= cum[i]).
-      if (tid == 0) {
-        uint32_t code = dec.code, range = dec.range;
-        int wofs = 0;                      // read offset into the staged window (s_win = stream[pos0 ...])
-        const int64_t pos0 = dec.pos;
-        for (int jj = 0; jj < npos; ++jj) {
-          const int hc = h_lo + jj, wc = u - 5 * hc;
-          if (hc < 0 || hc >= H || wc < 0 || wc >= W) continue;
-          const uint32_t* cumt = s_freq + jj * MAXL;
-          if (p.decode) {
-            const uint32_t r = range >> TOTAL_BITS;
-            uint32_t lo = 0;
-            int sy = 0;
-#pragma unroll
-            for (int i = 1; i < MAXL; ++i)  // thresholds ascend: the last one reached is the symbol
-              if (i < L) {
-                const uint32_t ci = cumt[i];
-                if (code >= r * ci) { sy = i; lo = ci; }  // r < 2^16 and ci < 2^16: the product fits 32 bits
-              }
-            const uint32_t hi = sy + 1 < L ? cumt[sy + 1] : TOTAL;
-            code -= lo * r;
-            range = r * (hi - lo);
-            while (range < (1u << 24)) {
-              const int64_t at = pos0 + wofs;
-              const uint32_t byte = wofs < WIN ? s_win[wofs] : (at < my_len ? my_stream[at] : 0);
-              ++wofs;
-              code = (code << 8) | byte;
-              range <<= 8;
-            }
-            sym[((size_t)d * H + hc) * W + wc] = sy;
-            *q_at(d, hc, wc) = s_cent[sy];
-          } else {
-            const int sy = s_sym[jj];
-            const uint32_t lo = cumt[sy], hi = sy + 1 < L ? cumt[sy + 1] : TOTAL;
-            enc.encode(lo, hi - lo);
-          }
-        }
-        if (p.decode) { dec.code = code; dec.range = range; dec.pos = pos0 + wofs; *s_pos = dec.pos; }
-      }
-      PC_MARK(7)
-      // the barrier at the top of the next step orders the coder's q writes before the next layer-0 reads
+      *s_pos = dec_pos;
+    } else {
+      enc.init(p.bytes + ((size_t)img * p.nstreams + stream) * p.cap, p.cap);
     }
-    __syncthreads();
-    if (tid == 32) st_release(progress + d, u_max);
   }
-  if (profiling)
-    for (int i = 0; i < 8; ++i) p.prof[i] = pf[i];
-  if (tid == 0 && !p.decode) {
+  __syncthreads();  // s_pos is read by the bulk warps
+
+  const bool is_coder = tid >= BULK;           // warp 9; only its first lane works
+  const int j = tid / 8, c3 = tid % 8;         // bulk thread: position j of the step, channels c3, c3 + 8, c3 + 16
+  const bool lane_ok = tid < MAXPOS * 8;       // 264 of the 288 bulk threads own outputs
+  const int u_min = 5 * -3 - 3, u_max = 5 * (H + 2) + (W + 2);
+  float p0[3] = {0.f, 0.f, 0.f}, p1[3] = {0.f, 0.f, 0.f}, p2[3] = {0.f, 0.f, 0.f}, p3[1] = {0.f};
+
+  // positions of step u: h in [h_lo, h_lo + npos), w = u - 5 h in [-3, W + 2]
+  auto positions = [&](int u, int& h_lo, int& npos) {
+    int lo = u - (W + 2);
+    lo = lo > 0 ? (lo + 4) / 5 : -((-lo) / 5);        // ceil
+    if (lo < -3) lo = -3;
+    int hi = u + 3;
+    hi = hi >= 0 ? hi / 5 : -((-hi + 4) / 5);         // floor
+    if (hi > H + 2) hi = H + 2;
+    h_lo = lo;
+    npos = hi - lo + 1;
+  };
+  // old taps (0..11) of every position of the step into shared memory: one L2 round trip per layer
+  auto gather_old = [&](auto at_fn, const float* kconst, int d, int u, int h_lo, int npos, int lo, int hiH, int hiW) {
+    const float4* k4 = reinterpret_cast<const float4*>(kconst);
+    float4* dst = reinterpret_cast<float4*>(s_in);
+    for (int idx = tid; idx < npos * 12 * (K / 4); idx += BULK) {
+      const int jj = idx / (12 * (K / 4)), r = idx % (12 * (K / 4));
+      const int t = r / (K / 4), g = r % (K / 4);
+      const int hh = h_lo + jj, ww = u - 5 * hh;
+      if (hh < lo || hh >= hiH || ww < lo || ww >= hiW) continue;
+      const int dd = t < 9 ? d - 1 : d;               // taps 0..8: previous slice; 9..11: row h - 1
+      const int dh = t < 9 ? t / 3 - 1 : -1;
+      const int dw = t < 9 ? t % 3 - 1 : t - 10;
+      dst[(jj * NT + t) * (K / 4) + g] =
+          dd < 0 ? k4[g] : __ldcg(reinterpret_cast<const float4*>(at_fn(dd, hh + dh, ww + dw)) + g);
+    }
+  };
+
+  // ---- bulk warps: partial chains (taps 0..11) of step u for all four layers
+  auto bulk_partials = [&](int d, int u) {
+    int h_lo, npos;
+    positions(u, h_lo, npos);
+    if (tid == 0 && d > 0) {  // slice d - 1 must be complete through step u + 6
+      const int need = u + 6 < u_max ? u + 6 : u_max;
+      while (ld_acquire(progress + d - 1) < need) __nanosleep(32);
+    }
+    bar_bulk();
+    const int h = h_lo + j, w = u - 5 * h;
+    const bool act = lane_ok && j < npos;
+    if (act) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) p0[c] = s_b0[c3 + 8 * c];
+#pragma unroll
+      for (int t = 0; t < 12; ++t) {
+        const int dd = d + c_taps[t][0];
+        const float x = dd < 0 ? pad : __ldcg(q_at(dd, h + c_taps[t][1], w + c_taps[t][2]));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p0[c] = __fmaf_rn(x, s_w0[t * K + c3 + 8 * c], p0[c]);
+      }
+    }
+    gather_old(a0_at, s_k0, d, u, h_lo, npos, -2, H + 2, W + 2);
+    bar_bulk();
+    if (act && h >= -2 && h < H + 2 && w >= -2 && w < W + 2) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) p1[c] = s_b1[c3 + 8 * c];
+#pragma unroll
+      for (int t = 0; t < 12; ++t) chain_tap<3>(p1, s_w1 + (t * K + c3) * KP, 8 * KP, s_in + (j * NT + t) * K);
+    }
+    bar_bulk();
+    gather_old(a1_at, s_k1, d, u, h_lo, npos, -1, H + 1, W + 1);
+    bar_bulk();
+    if (act && h >= -1 && h < H + 1 && w >= -1 && w < W + 1) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) p2[c] = s_b2[c3 + 8 * c];
+#pragma unroll
+      for (int t = 0; t < 12; ++t) chain_tap<3>(p2, s_w2 + (t * K + c3) * KP, 8 * KP, s_in + (j * NT + t) * K);
+    }
+    bar_bulk();
+    gather_old(a2_at, s_k2, d, u, h_lo, npos, 0, H, W);
+    bar_bulk();
+    if (act && c3 < L && h >= 0 && h < H && w >= 0 && w < W) {
+      p3[0] = s_b3[c3];
+#pragma unroll
+      for (int t = 0; t < 12; ++t) chain_tap<1>(p3, s_w3 + (t * MAXL + c3) * KP, 0, s_in + (j * NT + t) * K);
+    }
+  };
+
+  // ---- bulk warps: finish the chains of step u (taps 12, 13), store the activations, build the frequency tables
+  auto finish = [&](int d, int u) {
+    int h_lo, npos;
+    positions(u, h_lo, npos);
+    const int h = h_lo + j, w = u - 5 * h;
+    const bool act = lane_ok && j < npos;
+    const int par = u & 1, prev = par ^ 1;
+    float* c0 = s_c0 + (par * MAXH + h + 3) * K;
+    float* c1 = s_c1 + (par * MAXH + h + 3) * K;
+    float* c2 = s_c2 + (par * MAXH + h + 3) * K;
+    if (act) {  // layer 0: tap 12 = the centre decoded one step ago in this row (or padding)
+      const float x = (h >= 0 && h < H && w - 1 >= 0 && w - 1 < W) ? s_qc[h] : pad;
+      float* o = a0_at(d, h, w);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = relu(__fmaf_rn(x, s_w0[12 * K + c3 + 8 * c], p0[c]));
+        o[c3 + 8 * c] = v;
+        c0[c3 + 8 * c] = v;
+      }
+    }
+    bar_bulk();
+    if (act && h >= -2 && h < H + 2 && w >= -2 && w < W + 2) {
+      chain_tap<3>(p1, s_w1 + (12 * K + c3) * KP, 8 * KP, s_c0 + (prev * MAXH + h + 3) * K);
+      chain_tap<3>(p1, s_w1 + (13 * K + c3) * KP, 8 * KP, c0);
+      float* o = a1_at(d, h, w);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = relu(p1[c]);
+        o[c3 + 8 * c] = v;
+        c1[c3 + 8 * c] = v;
+      }
+    }
+    bar_bulk();
+    if (act && h >= -1 && h < H + 1 && w >= -1 && w < W + 1) {
+      chain_tap<3>(p2, s_w2 + (12 * K + c3) * KP, 8 * KP, s_c1 + (prev * MAXH + h + 3) * K);
+      chain_tap<3>(p2, s_w2 + (13 * K + c3) * KP, 8 * KP, c1);
+      float* o = a2_at(d, h, w);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = __fadd_rn(p2[c], c0[c3 + 8 * c]);  // + skip (layer-0 value of this position)
+        o[c3 + 8 * c] = v;
+        c2[c3 + 8 * c] = v;
+      }
+    }
+    bar_bulk();
+    if (act && c3 < L && h >= 0 && h < H && w >= 0 && w < W) {
+      chain_tap<1>(p3, s_w3 + (12 * MAXL + c3) * KP, 0, s_c2 + (prev * MAXH + h + 3) * K);
+      chain_tap<1>(p3, s_w3 + (13 * MAXL + c3) * KP, 0, c2);
+      s_logit[j * MAXL + c3] = relu(p3[0]);
+    }
+    bar_bulk();
+    // frequency tables (cumulative), one thread per position; other threads stage the coder's global reads
+    if (tid < npos) {
+      const int hf = h_lo + tid, wf = u - 5 * hf;
+      if (hf >= 0 && hf < H && wf >= 0 && wf < W) {
+        uint32_t f[MAXL];
+        logits_to_freqs(s_logit + tid * MAXL, L, f);
+        uint32_t c = 0;  // entry i = sum of f[0..i-1]; the last boundary (65536) is implied
+        for (int i = 0; i < L; ++i) {
+          s_freq[tid * MAXL + i] = c;
+          c += f[i];
+        }
+        if (!p.decode) s_sym[tid] = (int)sym[((size_t)d * H + hf) * W + wf];
+      }
+    } else if (p.decode && tid >= 64 && tid < 64 + WIN) {
+      const int64_t at = (int64_t)*s_pos + (tid - 64);
+      s_win[tid - 64] = at < my_len ? my_stream[at] : 0;
+    }
+  };
+
+  // ---- coder thread: the symbols of step u in increasing h.  Decoding is division-free: the symbol is the number of
+  // cumulative thresholds r * cum[i] the code value has reached (floor(code / r) >= cum[i]  <=>  code >= r * cum[i]).
+  auto coder = [&](int d, int u) {
+    int h_lo, npos;
+    positions(u, h_lo, npos);
+    int wofs = 0;                      // read offset into the staged window (s_win = stream[dec_pos ...])
+    for (int jj = 0; jj < npos; ++jj) {
+      const int hc = h_lo + jj, wc = u - 5 * hc;
+      if (hc < 0 || hc >= H || wc < 0 || wc >= W) continue;
+      const uint32_t* cumt = s_freq + jj * MAXL;
+      int sy;
+      if (p.decode) {
+        const uint32_t r = dec_range >> TOTAL_BITS;
+        uint32_t lo = 0;
+        sy = 0;
+#pragma unroll
+        for (int i = 1; i < MAXL; ++i)  // thresholds ascend: the last one reached is the symbol
+          if (i < L) {
+            const uint32_t ci = cumt[i];
+            if (dec_code >= r * ci) { sy = i; lo = ci; }  // r < 2^16 and ci < 2^16: the product fits 32 bits
+          }
+        const uint32_t hi = sy + 1 < L ? cumt[sy + 1] : TOTAL;
+        dec_code -= lo * r;
+        dec_range = r * (hi - lo);
+        while (dec_range < (1u << 24)) {
+          const int64_t at = dec_pos + wofs;
+          const uint32_t byte = wofs < WIN ? s_win[wofs] : (at < my_len ? my_stream[at] : 0);
+          ++wofs;
+          dec_code = (dec_code << 8) | byte;
+          dec_range <<= 8;
+        }
+        sym[((size_t)d * H + hc) * W + wc] = sy;
+        *q_at(d, hc, wc) = s_cent[sy];
+      } else {
+        sy = s_sym[jj];
+        const uint32_t lo = cumt[sy], hi = sy + 1 < L ? cumt[sy + 1] : TOTAL;
+        enc.encode(lo, hi - lo);
+      }
+      s_qc[hc] = s_cent[sy];
+    }
+    if (p.decode) {
+      dec_pos += wofs;
+      *s_pos = dec_pos;
+    }
+  };
+
+  for (int d = stream; d < C; d += p.nstreams) {
+    if (!is_coder) {  // fill the pipeline: the first step of the slice has no coder work before it
+      bulk_partials(d, u_min);
+      bar_bulk();
+      finish(d, u_min);
+    }
+    for (int u = u_min; u <= u_max; ++u) {
+      __syncthreads();  // tables of step u are ready; everything of earlier steps is written
+      if (is_coder) {
+        if (tid == BULK) coder(d, u);
+      } else if (u < u_max) {
+        bulk_partials(d, u + 1);
+      }
+      __syncthreads();  // symbols of step u are coded; partial chains of step u + 1 sit in registers
+      if (tid == 32) st_release(progress + d, u);  // step u is complete: publish it off the critical path
+      if (!is_coder && u < u_max) finish(d, u + 1);
+    }
+  }
+  if (tid == BULK && !p.decode) {
     enc.flush();
     p.sizes[(size_t)img * p.nstreams + stream] = enc.pos;
     if (enc.overflow) atomicExch(p.status, 1);
@@ -499,7 +499,7 @@ Layout layout(int n, int c, int h, int w) {
 constexpr size_t kSmemBytes =
     (size_t)(2 * NT * K * KP + NT * MAXL * KP + NT0 * K + 3 * K + MAXL + 3 * K + MAXL + MAXPOS * MAXL) * sizeof(float) +
     (size_t)MAXPOS * MAXL * sizeof(uint32_t) + (size_t)MAXPOS * NT * K * sizeof(float) +
-    (size_t)(MAXPOS + 1) * sizeof(int) + sizeof(long long) + WIN;
+    (size_t)(3 * 2 * MAXH * K + MAXH) * sizeof(float) + (size_t)(MAXPOS + 1) * sizeof(int) + sizeof(long long) + WIN;
 
 int run_codec(dsin_handle_t h, int decode, int64_t* symbols, int n, int c, int hh, int ww, const float* centers, int L,
               const float* const* wb, int k, int nstreams, uint8_t* bytes, int64_t cap, int64_t* sizes, int* status_out,
@@ -510,6 +510,7 @@ int run_codec(dsin_handle_t h, int decode, int64_t* symbols, int n, int c, int h
   DSIN_REQUIRE(h, L >= 2 && L <= MAXL, "2..8 centres");
   DSIN_REQUIRE(h, nstreams >= 1 && nstreams <= 64, "1..64 streams per image");
   DSIN_REQUIRE(h, (ww + 5) / 5 + 1 <= MAXPOS, "volume wider than 159 symbols (one CTA walks a slice 33 positions at a time)");
+  DSIN_REQUIRE(h, hh + 6 <= MAXH, "volume taller than 58 symbols (rows of the shared-memory rings)");
   static const bool wavefront_encode = getenv("DSIN_PC_ENCODE_WAVEFRONT") != nullptr;
   if (!decode && !wavefront_encode && L == 6 && (ww + 4) / 5 + 1 <= 32) {
     // every symbol is known: frequency tables for the whole volume in parallel (probclass.cu), then one CTA per
@@ -556,23 +557,11 @@ int run_codec(dsin_handle_t h, int decode, int64_t* symbols, int n, int c, int h
     a.bytes = bytes + (size_t)i0 * nstreams * cap; a.cap = cap; a.sizes = sizes + (size_t)i0 * nstreams;
     pc_codec_prepare_kernel<<<h->sm_count * 4, 256, 0, st>>>(a);
     DSIN_LAUNCHED(h);
-    static const bool want_prof = getenv("DSIN_PC_PROFILE") != nullptr;
-    long long* prof = nullptr;
-    if (want_prof && cudaMallocManaged(&prof, 8 * sizeof(long long)) == cudaSuccess) {
-      memset(prof, 0, 8 * sizeof(long long));
-      a.prof = prof;
-    }
     void* params[] = {&a};
     if (cudaLaunchCooperativeKernel((const void*)pc_codec_kernel, dim3(ni * nstreams), dim3(THREADS), params, kSmemBytes,
                                     st) != cudaSuccess)
       return dsin_fail(h, DSIN_ERR_CUDA, "%s: cooperative launch failed (are all CTAs co-resident?)", __func__);
     DSIN_LAUNCHED(h);
-    if (prof) {  // debugging aid only: synchronises
-      cudaStreamSynchronize(st);
-      fprintf(stderr, "pc_codec phases (cycles of one CTA): wait %lld | L0 %lld | gather1 %lld | L1 %lld | L2 %lld | logits %lld | "
-                      "freq %lld | coder %lld\n", prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], prof[6], prof[7]);
-      cudaFree(prof);
-    }
   }
   return DSIN_OK;
 }
