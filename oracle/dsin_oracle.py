@@ -10,9 +10,10 @@ fixtures, and TensorFlow 1.11 cannot be installed here, so the TF op semantics
 restated below (SAME padding, FusedBatchNorm inference, Conv3D, ExtractImagePatches,
 CropAndResize, ArgMax tie-breaking, softmax cross entropy) are pinned only by the TF
 documentation/kernels as summarised in SURVEY.md App. A.  The two pieces of the
-reference that *do* run here -- ``AE.create_gaussian_masks`` (pure numpy) and
-``ms_ssim_np_imgcomp`` (numpy/scipy) -- are pinned by ``tests/golden`` fixtures that
-were generated from the reference itself (``tests/golden/make_golden.py``).
+reference that *do* run here -- ``AE.create_gaussian_masks`` (pure numpy), ``ms_ssim_np_imgcomp``
+(numpy/scipy) and the numpy-only pieces of the model code (causal conv masks, symbol-volume padding,
+``AE.normalize``/``denormalize``/``get_mean_var``, the coder helpers' block order) -- are pinned by
+``tests/golden`` fixtures that were generated from the reference itself (``tests/golden/make_golden.py``).
 
 All citations are ``file:line`` relative to /root/reference/.
 Weights are a flat ``dict[str, np.ndarray]`` keyed by the TF variable names of

@@ -6,6 +6,10 @@ Run here (needs /root/reference):  python tests/golden/make_golden.py
   * msssim_golden.npz - ms_ssim_np_imgcomp.MultiScaleSSIM / utils.msssim_x_vs_rec call forms
                         (src/ms_ssim_np_imgcomp.py, src/utils.py:94-99) with ``tensorflow``
                         stubbed in sys.modules (the module never uses it).
+  * model_pieces_golden.npz - the numpy-only pieces of the model code, extracted with ``ast`` and run with a stub
+                        ``tf.name_scope``: the causal conv masks (src/probclass_imgcomp.py:150-176), the symbol
+                        volume padding and its inverse (:268-292, :341-353), the block iteration order of the coder
+                        helpers (:371-393) and AE.normalize / denormalize / get_mean_var (src/AE.py:222-250).
 Nothing from the reference is copied into the repo; only its numeric outputs are stored.
 """
 import ast
@@ -70,8 +74,56 @@ def make_msssim():
     np.savez_compressed(os.path.join(OUT, "msssim_golden.npz"), **out)
 
 
+def _extract(path, names):
+    """Compile the named functions / methods of a reference file in isolation (no module import)."""
+    import contextlib
+    import functools
+    import itertools
+    tree = ast.parse(open(os.path.join(REF, path)).read())
+    body = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name in names]
+    for n in body:
+        n.decorator_list = []  # staticmethod / property decorators are meaningless outside the class
+    tf_stub = types.SimpleNamespace(name_scope=lambda *_a, **_k: contextlib.nullcontext(), Variable=type(None))
+    ns = {"np": np, "tf": tf_stub, "functools": functools, "itertools": itertools,
+          "_Network3D": types.SimpleNamespace(_make_tf_conv3d_mask=lambda m: m)}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
+def make_model_pieces():
+    pc = _extract("probclass_imgcomp.py", {
+        "create_first_mask", "create_other_mask", "pad_for_probclass3d", "undo_pad_for_probclass3d", "get_np_pad_fn",
+        "add_batch_dim", "remove_batch_dim", "_get_ndims", "iter_over_blocks", "num_blocks", "_iter_block_idices",
+        "context_shape_from_context_size", "context_size_from_context_shape"})
+    out = {}
+    net = types.SimpleNamespace(config=types.SimpleNamespace(kernel_size=3), filter_shape=(2, 3, 3))
+    out["first_mask"] = pc["create_first_mask"](net)    # (2,3,3,1,1)
+    out["other_mask"] = pc["create_other_mask"](net)
+    rng = np.random.default_rng(5)
+    vol = rng.normal(size=(2, 3, 4, 5)).astype(np.float32)             # NCHW
+    out["pad_in"] = vol
+    out["pad_out_cs9"] = pc["pad_for_probclass3d"](vol, 9, 1.5)
+    out["pad_out_chw_cs5"] = pc["pad_for_probclass3d"](vol[0], 5, -0.25)
+    out["unpad_cs9"] = pc["undo_pad_for_probclass3d"](out["pad_out_cs9"][0], 9)  # CHW numpy branch
+    out["context_shape_9"] = np.array(pc["context_shape_from_context_size"](9))
+    syms = np.arange(4 * 5 * 6).reshape(4, 5, 6)
+    blocks = list(pc["iter_over_blocks"](syms, (2, 3, 3)))
+    out["block_first_elems"] = np.array([b[0, 0, 0] for b in blocks])
+    out["block_count"] = np.array(pc["num_blocks"](syms.shape, (2, 3, 3)))
+    ae = _extract("AE.py", {"normalize", "denormalize", "get_mean_var"})
+    stub = types.SimpleNamespace(ae_config=types.SimpleNamespace(normalization="FIXED"), get_mean_var=ae["get_mean_var"])
+    img = rng.integers(0, 256, size=(2, 3, 6, 7)).astype(np.float32)
+    out["norm_in"] = img
+    out["norm_out"] = ae["normalize"](stub, img)
+    out["denorm_out"] = ae["denormalize"](stub, out["norm_out"])
+    mean, var = ae["get_mean_var"]()
+    out["mean"], out["var"] = mean, var
+    np.savez_compressed(os.path.join(OUT, "model_pieces_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     make_masks()
     make_msssim()
-    for f in ("mask_golden.npz", "msssim_golden.npz"):
+    make_model_pieces()
+    for f in ("mask_golden.npz", "msssim_golden.npz", "model_pieces_golden.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)))

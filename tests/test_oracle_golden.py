@@ -153,3 +153,35 @@ def test_crop_and_resize_coordinates():
     assert out[0, 0, 0, 0] == pytest.approx(99.6875, abs=1e-4)
     assert out[0, 1, 0, 0] == pytest.approx(100.7368, abs=1e-3)
     assert out[0, 2, 0, 0] == pytest.approx(101.7862, abs=1e-3)
+
+
+def test_model_pieces_match_reference(golden_dir):
+    """Numpy-only pieces of the reference's model code, executed from the reference itself by
+    tests/golden/make_golden.py: causal masks, symbol-volume padding, normalisation, coder block order."""
+    import torch.nn.functional as F
+    from dsin_b200 import probclass_imgcomp as product_pc
+    from oracle import pc_codec as P
+    g = np.load(os.path.join(golden_dir, "model_pieces_golden.npz"))
+    first, other = O.pc_masks(3)
+    assert np.array_equal(first, g["first_mask"][..., 0, 0]) and np.array_equal(other, g["other_mask"][..., 0, 0])
+    pf, po = product_pc.create_masks(3)
+    assert np.array_equal(pf, first) and np.array_equal(po, other)
+    # the entropy coder's live-tap lists are exactly the non-zero mask entries in raster (kd, kh, kw) order
+    live = lambda m: [tuple(int(v) for v in idx) for idx in np.argwhere(m != 0)]  # noqa: E731
+    assert P.TAPS_FIRST == live(first) and P.TAPS_OTHER == live(other)
+    # padding of the symbol volume: front of the depth axis and both sides of H, W; nothing behind in depth
+    x = torch.from_numpy(g["pad_in"])
+    assert np.array_equal(F.pad(x, (4, 4, 4, 4, 4, 0), value=1.5).numpy(), g["pad_out_cs9"])
+    assert np.array_equal(F.pad(x[0], (2, 2, 2, 2, 2, 0), value=-0.25).numpy(), g["pad_out_chw_cs5"])
+    assert np.array_equal(g["unpad_cs9"], g["pad_in"][0]) and list(g["context_shape_9"]) == [5, 9, 9]
+    # normalisation constants and arithmetic (float32, sqrt(var + 1e-10) evaluated in float32)
+    assert np.array_equal(O.KITTI_MEAN, g["mean"].reshape(3)) and np.array_equal(O.KITTI_VAR, g["var"].reshape(3))
+    from dsin_b200.AE import AE
+    pm, pv = AE.get_mean_var()
+    assert np.array_equal(pm, g["mean"]) and np.array_equal(pv, g["var"])
+    n = O.normalize(torch.from_numpy(g["norm_in"]))
+    assert np.array_equal(n.numpy(), g["norm_out"])
+    assert np.array_equal(O.denormalize(torch.from_numpy(g["norm_out"])).numpy(), g["denorm_out"])
+    # the coder helpers walk the symbol volume with W fastest, then H, then C (src/probclass_imgcomp.py:383-393)
+    want = [c * 30 + h * 6 + w for c in range(3) for h in range(3) for w in range(4)]
+    assert g["block_first_elems"].tolist() == want and int(g["block_count"]) == 36
