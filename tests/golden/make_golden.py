@@ -9,7 +9,9 @@ Run here (needs /root/reference):  python tests/golden/make_golden.py
   * model_pieces_golden.npz - the numpy-only pieces of the model code, extracted with ``ast`` and run with a stub
                         ``tf.name_scope``: the causal conv masks (src/probclass_imgcomp.py:150-176), the symbol
                         volume padding and its inverse (:268-292, :341-353), the block iteration order of the coder
-                        helpers (:371-393) and AE.normalize / denormalize / get_mean_var (src/AE.py:222-250).
+                        helpers (:371-393), AE.normalize / denormalize / get_mean_var (src/AE.py:222-250), and the
+                        host helpers readfiles (src/DataProvider.py:96-100), l1_x_vs_rec and save_test_imgs_fn
+                        (src/utils.py:82-111).
 Nothing from the reference is copied into the repo; only its numeric outputs are stored.
 """
 import ast
@@ -118,6 +120,27 @@ def make_model_pieces():
     out["denorm_out"] = ae["denormalize"](stub, out["norm_out"])
     mean, var = ae["get_mean_var"]()
     out["mean"], out["var"] = mean, var
+    # host-side helpers: pair-list reader (src/DataProvider.py:96-100), L1 metric and PNG writer (src/utils.py:82-111)
+    import tempfile
+    from PIL import Image
+    dp = _extract("DataProvider.py", {"readfiles"})
+    ut = _extract("utils.py", {"l1_x_vs_rec", "save_test_imgs_fn"})
+    ut["os"], ut["Image"] = os, Image
+    with tempfile.TemporaryDirectory() as tmp:
+        lst = os.path.join(tmp, "pairs.txt")
+        with open(lst, "w") as f:
+            f.write("a/image_2/000000_10.png\na/image_3/000000_10.png\n  b/x.png  \nb/y.png\n")
+        out["readfiles"] = np.array(dp["readfiles"](types.SimpleNamespace(root_data="/data/"), lst))
+        rec = rng.uniform(-3, 260, size=(3, 5, 8)).astype(np.float32).clip(0, 255)
+        ut["save_test_imgs_fn"](tmp + "/", "model", rec, 7, 0.0312345)
+        name = os.listdir(os.path.join(tmp, "model"))
+        out["png_name"] = np.array(name)
+        out["png_in"] = rec
+        out["png_pixels"] = np.asarray(Image.open(os.path.join(tmp, "model", name[0])))
+    a = rng.integers(0, 256, size=(6, 7, 3)).astype(np.uint8)
+    b = rng.uniform(0, 255, size=(6, 7, 3)).astype(np.float32)
+    diff, l1 = ut["l1_x_vs_rec"](a, b)
+    out["l1_a"], out["l1_b"], out["l1_diff"], out["l1_value"] = a, b, diff, np.float32(l1)
     np.savez_compressed(os.path.join(OUT, "model_pieces_golden.npz"), **out)
 
 

@@ -185,3 +185,22 @@ def test_model_pieces_match_reference(golden_dir):
     # the coder helpers walk the symbol volume with W fastest, then H, then C (src/probclass_imgcomp.py:383-393)
     want = [c * 30 + h * 6 + w for c in range(3) for h in range(3) for w in range(4)]
     assert g["block_first_elems"].tolist() == want and int(g["block_count"]) == 36
+
+
+def test_host_helpers_match_reference(golden_dir, tmp_path):
+    """Pair-list reader, PNG writer (name + uint8 truncation) and L1 metric against the reference's own functions
+    (src/DataProvider.py:96-100, src/utils.py:82-111), executed by tests/golden/make_golden.py."""
+    import types
+    from PIL import Image
+    from dsin_b200 import utils
+    from dsin_b200.DataProvider import Dataset
+    g = np.load(os.path.join(golden_dir, "model_pieces_golden.npz"))
+    lst = tmp_path / "pairs.txt"
+    lst.write_text("a/image_2/000000_10.png\na/image_3/000000_10.png\n  b/x.png  \nb/y.png\n")
+    got = Dataset.readfiles(types.SimpleNamespace(root_data="/data/"), str(lst))
+    assert got == g["readfiles"].tolist()
+    utils.save_test_imgs_fn(str(tmp_path) + "/", "model", g["png_in"], 7, 0.0312345)
+    assert os.listdir(tmp_path / "model") == g["png_name"].tolist()
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "model" / str(g["png_name"][0]))), g["png_pixels"])
+    diff, l1 = utils.l1_x_vs_rec(g["l1_a"], g["l1_b"])
+    assert np.array_equal(diff, g["l1_diff"]) and np.float32(l1) == g["l1_value"]
