@@ -458,6 +458,50 @@ def run_codec(args, rank, world, local_rank):
     }), flush=True)
 
 
+def run_roundtrip(args, rank, world, local_rank):
+    """Sender and receiver with real bitstreams through the public numpy API: compress(x) -> bytes;
+    decompress(bytes, y) -> y_dec, y_syn, x_dec, x_with_si (host buffers on both sides)."""
+    import torch
+    import __graft_entry__ as g
+    torch.cuda.set_device(local_rank)
+    g.build()
+    from dsin_b200 import synth
+    B = args.batch
+    ae = build_ae(local_rank)
+    x, y = synth.make_batch(B, H, W, seed=1000)
+    x8, y8 = x.astype(np.uint8), y.astype(np.uint8)
+    for _ in range(args.warmup):
+        blobs = ae.compress(x8, nstreams=args.streams)
+        ae.decompress(blobs, y8)
+    torch.cuda.synchronize()
+    t_enc = t_dec = 0.0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        blobs = ae.compress(x8, nstreams=args.streams)
+        t1 = time.perf_counter()
+        y_dec, y_syn, x_dec, x_with_si = ae.decompress(blobs, y8)
+        t2 = time.perf_counter()
+        t_enc += t1 - t0
+        t_dec += t2 - t1
+    ref = ae.siNet_get_reconstructed(x8, y8)
+    if rank != 0:
+        return
+    mpix = B * args.steps * H * W * 1e-6
+    nbytes = sum(len(b) for b in blobs)
+    print(json.dumps({
+        "metric": METRIC + " -- sender/receiver with real bitstreams", "value": mpix / t_dec, "unit": "Mpixels/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dec / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": ae_dtype(), "data": "synthetic",
+        "config": {"workload": "receiver: decompress(bitstreams, y) = PC1 decode + AE(y) + decoder(x) + SI-Finder + SI-Net, "
+                               "batch %d of 320x1224, %d streams per image; sender timed beside it" % (B, args.streams),
+                   "batch_per_gpu": B, "streams": args.streams},
+        "sender_ms_per_step": t_enc / args.steps * 1e3, "sender_mpix_s": mpix / t_enc,
+        "receiver_ms_per_step": t_dec / args.steps * 1e3, "receiver_mpix_s": mpix / t_dec,
+        "bitstream_bytes_per_batch": nbytes, "bpp_real": 8.0 * nbytes / (B * H * W), "bpp_estimate": float(ref[4]),
+        "max_abs_diff_x_with_si_vs_one_call": float(np.abs(np.array(x_with_si) - np.array(ref[3])).max()),
+    }), flush=True)
+
+
 def ae_dtype():
     from dsin_b200 import autoencoder_imgcomp
     return getattr(autoencoder_imgcomp, "COMPUTE_DTYPE", "f32")
@@ -472,7 +516,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=8, help="range-coder streams per image (--workload codec)")
-    ap.add_argument("--workload", default="full", choices=["full", "sif", "codec"],
+    ap.add_argument("--workload", default="full", choices=["full", "sif", "codec", "roundtrip"],
                     help="full = BASELINE configs[1]; sif = configs[2] (SI-Finder in isolation, use --batch 32)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -488,6 +532,9 @@ def main():
         return
     if args.workload == "codec":
         run_codec(args, rank, world, local_rank)
+        return
+    if args.workload == "roundtrip":
+        run_roundtrip(args, rank, world, local_rank)
         return
     run_ours(args, rank, world, local_rank)
 
