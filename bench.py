@@ -176,9 +176,18 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         g.build()
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dist.barrier()
+        # NCCL writes its version / debug lines to the C-level stdout when NCCL_DEBUG is set in the environment:
+        # point fd 1 at stderr while the communicator comes up, so that stdout carries the one JSON line only
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     if rank != 0:
         g.build()  # no-op: rank 0 has built; this only loads/validates the library
     from dsin_b200 import ops, synth
