@@ -238,16 +238,65 @@ extern "C" int dsin_probclass_bits(dsin_handle_t h, const float* qbar, const int
 // conv (3-D VALID mode, channels padded 24 -> 32, split fp16); the 1->24 stem and the 24->6 layer with
 // its fused cross entropy stay on CUDA cores.
 // ---------------------------------------------------------------------------------------------
-__global__ void pc_pad_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
-                                    int64_t nvox, int cin, int cpad) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nvox * cpad) return;
-  int c = (int)(idx % cpad);
-  int64_t v = idx / cpad;
-  float f = c < cin ? x[v * cin + c] : 0.f;
-  __half h = __float2half_rn(f);
-  hi[idx] = h;
-  lo[idx] = __float2half_rn(f - __half2float(h));
+// Stem of the tensor-core path: layer 0 (1 -> 24, the arithmetic of pc_conv3d_kernel<1, 24, true, false>) with
+// both of its consumers' formats written at once -- fp32 (the skip of res1/conv2) and 32-channel split fp16 (the
+// operand of res1/conv1).  A block owns 128 consecutive voxels and writes them as contiguous 16-byte pieces.
+__global__ void __launch_bounds__(128) pc_stem_split_kernel(PcP p, __half* __restrict__ hi, __half* __restrict__ lo) {
+  __shared__ float s_w[18 * 24 + 24];
+  __shared__ __align__(16) float s_out[128 * 24];
+  for (int i = threadIdx.x; i < 18 * 24 + 24; i += blockDim.x) s_w[i] = i < 18 * 24 ? p.w[i] : p.b[i - 18 * 24];
+  __syncthreads();
+  const float* s_b = s_w + 18 * 24;
+  const int Do = p.Di - 1, Ho = p.Hi - 2, Wo = p.Wi - 2;
+  const int64_t total = (int64_t)p.n * Do * Ho * Wo;
+  const int64_t v0 = (int64_t)blockIdx.x * 128;
+  const int64_t idx = v0 + threadIdx.x;
+  if (idx < total) {
+    const int wq = (int)(idx % Wo);
+    int64_t t = idx / Wo;
+    const int hq = (int)(t % Ho);
+    t /= Ho;
+    const int dq = (int)(t % Do), img = (int)(t / Do);
+    float acc[24];
+#pragma unroll
+    for (int o = 0; o < 24; ++o) acc[o] = 0.f;
+#pragma unroll
+    for (int tp = 0; tp < 18; ++tp) {
+      if (!((p.live_mask >> tp) & 1u)) continue;
+      const int cc = dq + tp / 9 - 4, yy = hq + (tp / 3) % 3 - 4, xx = wq + tp % 3 - 4;
+      float v = p.pad_value;
+      if (cc >= 0 && yy >= 0 && yy < p.hh && xx >= 0 && xx < p.ww)
+        v = __ldg(p.in + (((int64_t)img * p.c + cc) * p.hh + yy) * p.ww + xx);
+      const float* wt = s_w + tp * 24;
+#pragma unroll
+      for (int o = 0; o < 24; ++o) acc[o] = fmaf(v, wt[o], acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < 24; ++o) s_out[threadIdx.x * 24 + o] = fmaxf(__fadd_rn(acc[o], s_b[o]), 0.f);
+  }
+  __syncthreads();
+  const int nv = (int)min((int64_t)128, total - v0);
+  float4* o4 = reinterpret_cast<float4*>(p.out + v0 * 24);
+  for (int e = threadIdx.x; e < nv * 6; e += blockDim.x) o4[e] = reinterpret_cast<const float4*>(s_out)[e];
+  uint4* h4 = reinterpret_cast<uint4*>(hi + v0 * 32);
+  uint4* l4 = reinterpret_cast<uint4*>(lo + v0 * 32);
+  for (int e = threadIdx.x; e < nv * 4; e += blockDim.x) {  // 8 channels per piece; channels 24..31 are zero padding
+    const int vox = e / 4, c8 = (e % 4) * 8;
+    uint4 uh = make_uint4(0u, 0u, 0u, 0u), ul = make_uint4(0u, 0u, 0u, 0u);
+    if (c8 < 24) {
+      __half2* hh2 = reinterpret_cast<__half2*>(&uh);
+      __half2* ll2 = reinterpret_cast<__half2*>(&ul);
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+        const float f0 = s_out[vox * 24 + c8 + 2 * k2], f1 = s_out[vox * 24 + c8 + 2 * k2 + 1];
+        const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
+        hh2[k2] = __halves2half2(h0, h1);
+        ll2[k2] = __halves2half2(__float2half_rn(f0 - __half2float(h0)), __float2half_rn(f1 - __half2float(h1)));
+      }
+    }
+    h4[e] = uh;
+    l4[e] = ul;
+  }
 }
 
 // cross entropy of 6 ReLU'd logits against the target symbol, in bits, + per-image fp64 sums
@@ -321,7 +370,6 @@ extern "C" int dsin_probclass_bits_tc(dsin_handle_t h, const float* qbar, const 
                "null weights");
   DSIN_REQUIRE(h, hh >= 8 && ww >= 16, "volume smaller than one tile");
   cudaStream_t st = (cudaStream_t)stream;
-  const int k = 24;
   int64_t v0 = (int64_t)n * (c + 3) * (hh + 6) * (ww + 6);
   int64_t v1 = (int64_t)n * (c + 2) * (hh + 4) * (ww + 4);
   int64_t v2 = (int64_t)n * (c + 1) * (hh + 2) * (ww + 2);
@@ -342,9 +390,7 @@ extern "C" int dsin_probclass_bits_tc(dsin_handle_t h, const float* qbar, const 
   // layer 0 (CUDA cores): padded (c+4, hh+8, ww+8, 1) -> (c+3, hh+6, ww+6, 24), ReLU
   p.in = qbar; p.w = w0; p.b = b0; p.out = a0; p.Di = c + 4; p.Hi = hh + 8; p.Wi = ww + 8;
   p.live_mask = pc_live_mask(true); p.relu = 1;
-  pc_conv3d_kernel<1, 24, true, false><<<(unsigned)((v0 + 127) / 128), 128, (18 * 24 + 24) * sizeof(float), st>>>(p);
-  DSIN_LAUNCHED(h);
-  pc_pad_split_kernel<<<(unsigned)((v0 * 32 + 255) / 256), 256, 0, st>>>(a0, x1h, x1l, v0, k, 32);
+  pc_stem_split_kernel<<<(unsigned)((v0 + 127) / 128), 128, 0, st>>>(p, x1h, x1l);
   DSIN_LAUNCHED(h);
   // res1/conv1 (tcgen05): ReLU, 32-channel (24 + 8 zero) split output
   ConvTc3dArgs a;

@@ -297,27 +297,36 @@ __global__ void sif_pack_q_kernel(const float* __restrict__ q, const float* __re
   }
 }
 
-// S_l[i][x] = fp16 {v[8l..8l+7]}, v[k] = r(i + k/3, x, k%3), for every correlation row i in [0, hp)
-__global__ void sif_pack_strip_kernel(const float* __restrict__ r, __half* __restrict__ s, int n, int hh,
-                                      int ww, int ph) {
+// S_l[i][x] = fp16 {v[8l..8l+7]}, v[k] = r(i + k/3, x, k%3), for every correlation row i in [0, hp).
+// A block stages the (PS_ROWS + ph - 1) x PS_COLS window of r it needs once (every element of r feeds up to ph
+// output rows), then writes 16-byte pixels, coalesced along x.
+constexpr int PS_ROWS = 16, PS_COLS = 64, PS_MAXPH = 24;
+__global__ void __launch_bounds__(256) sif_pack_strip_kernel(const float* __restrict__ r, __half* __restrict__ s, int n,
+                                                             int hh, int ww, int ph) {
+  __shared__ float tile[(PS_ROWS + PS_MAXPH - 1) * PS_COLS * 3];
   const int hp = hh - ph + 1;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (img, layer, i, x)
-  if (idx >= (int64_t)n * PAIRS * hp * ww) return;
-  const int x = (int)(idx % ww);
-  int64_t t = idx / ww;
-  const int i = (int)(t % hp);
-  t /= hp;
-  const int l = (int)(t % PAIRS);
-  const int img = (int)(t / PAIRS);
-  __half hv[8];
-#pragma unroll
-  for (int q8 = 0; q8 < 8; ++q8) {
-    const int k = 8 * l + q8;
-    float v = 0.f;
-    if (k < ph * 3) v = r[(((int64_t)img * hh + i + k / 3) * ww + x) * 3 + (k % 3)];
-    hv[q8] = __float2half_rn(v);
+  const int xb = blockIdx.x * PS_COLS, ib = blockIdx.y * PS_ROWS, img = blockIdx.z;
+  const int rows = min(PS_ROWS, hp - ib) + ph - 1;         // input rows ib .. ib + rows - 1 (all < hh)
+  const int cols = min(PS_COLS, ww - xb);
+  const float* src = r + ((int64_t)img * hh + ib) * ww * 3;
+  for (int e = threadIdx.x; e < rows * cols * 3; e += blockDim.x) {
+    const int row = e / (cols * 3), c = e % (cols * 3);
+    tile[row * PS_COLS * 3 + c] = src[(int64_t)row * ww * 3 + xb * 3 + c];
   }
-  reinterpret_cast<uint4*>(s)[idx] = *reinterpret_cast<const uint4*>(hv);
+  __syncthreads();
+  const int nout = min(PS_ROWS, hp - ib);
+  for (int o = threadIdx.x; o < PAIRS * nout * cols; o += blockDim.x) {
+    const int x = o % cols, i = (o / cols) % nout, l = o / (cols * nout);
+    __half hv[8];
+#pragma unroll
+    for (int q8 = 0; q8 < 8; ++q8) {
+      const int k = 8 * l + q8;
+      const float v = k < ph * 3 ? tile[((i + k / 3) * PS_COLS + x) * 3 + (k % 3)] : 0.f;
+      hv[q8] = __float2half_rn(v);
+    }
+    const int64_t idx = (((int64_t)img * PAIRS + l) * hp + ib + i) * ww + xb + x;
+    reinterpret_cast<uint4*>(s)[idx] = *reinterpret_cast<const uint4*>(hv);
+  }
 }
 
 // ---- exact rescoring: one warp per (image, patch) ------------------------------------------------
@@ -407,8 +416,9 @@ int sif_tc_match(dsin_handle_t h, const float* q, const float* r, const float* p
   const int64_t np = (int64_t)n * P;
   sif_pack_q_kernel<<<(unsigned)((np * 32 + 255) / 256), 256, 0, st>>>(q, pstat, q2, pinfo, n, P, ph, pw, hh, ww);
   DSIN_LAUNCHED(h);
-  const int64_t ns = (int64_t)n * PAIRS * hp * ww;
-  sif_pack_strip_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(r, strip, n, hh, ww, ph);
+  DSIN_REQUIRE(h, ph <= PS_MAXPH, "patch height above 24");
+  sif_pack_strip_kernel<<<dim3((ww + PS_COLS - 1) / PS_COLS, (hp + PS_ROWS - 1) / PS_ROWS, n), 256, 0, st>>>(r, strip, n, hh,
+                                                                                                      ww, ph);
   DSIN_LAUNCHED(h);
 
   CUtensorMap tm_q, tm_s;
