@@ -49,16 +49,51 @@ def peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in-process every 10 ms (an nvidia-smi
+    child needs longer to start than a short timed region lasts); nvidia-smi -lms as the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.proc, self.nvml, self.handle = gpu_index, [], None, None, None
+        self.sm, self.mx, self.reasons, self._stop = [], None, set(), False
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:  # the CUDA ordinal is not the NVML index when CUDA_VISIBLE_DEVICES remaps devices
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:  # noqa: BLE001
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                mask = int(get_reasons(self.handle))
+                for name, bit in self.BITS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -73,6 +108,11 @@ class ClockSampler(object):
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop = True
+            self.thread.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -92,7 +132,7 @@ class ClockSampler(object):
             except Exception:  # noqa: BLE001
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def cpu_info():
@@ -220,32 +260,49 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
 
     # ---------------- device-resident timing ----------------
+    # The timed steps replay the CUDA graphs the public call uses (inputs already in HBM, copied device-to-device
+    # into the captured input buffers): eager launching of ~230 kernels per step is host-bound when eight ranks
+    # share a busy host.  The per-kernel breakdown comes from a profiled eager pass right after the timed region.
+    step_device(0)  # first eager step also packs the weights; count the kernels of a steady-state step
+    l_step0 = ops.launch_count()
+    step_device(1)
+    launches_per_step = ops.launch_count() - l_step0
+
+    def step_graph(i):
+        xd, yd = dev_sets[i % NSETS]
+        return ae.replay_device(xd, yd)
+
     for i in range(args.warmup):
-        out = step_device(i)
+        out = step_graph(i)
     sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = ops.launch_count()
-    ops.PROF.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
     bits_total, npix_total = 0.0, 0
     outs = []
     for i in range(args.steps):
-        out = step_device(i)
-        outs.append(out["bits_sum"])
+        out = step_graph(i)
+        outs.append(out["bits_sum"].clone())  # graph outputs are static buffers
     e1.record()
     sync_all()
-    ops.PROF.stop()
     ms = e0.elapsed_time(e1)
-    launches = ops.launch_count() - l0
+    launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
-    prof = ops.PROF.summary()
     for bs in outs:
         bits_total += float(bs.sum().item())
         npix_total += B * H * W
+    # profiled eager pass: CUDA events around every kernel call on the launching stream
+    prof_steps = min(args.steps, 3)
+    sync_all()
+    ops.PROF.start()
+    for i in range(prof_steps):
+        step_device(i)
+    torch.cuda.synchronize()
+    ops.PROF.stop()
+    prof = ops.PROF.summary()
 
     # ---------------- decode-side region: receiver only, qbar(x) and y given ----------------
     qb_sets = [ae.reconstruct_device(*dev_sets[s_])["qbar"].clone() for s_ in range(NSETS)]
@@ -299,7 +356,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- roofline of the dominant kernel ----------------
     top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else None
-    kern = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+    kern = {k: {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] / prof_steps,
                 "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else None}
             for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
     roof = None
@@ -318,7 +375,9 @@ def run_ours(args, rank, world, local_rank):
                 "peak_source": pk["src"] + " bf16 dense sustained (fp16 shares the rate)",
                 "mma_terms_per_product": mma_terms, "frac_counting_issued_mma_work": mma_terms * ach / pk["tf_sust"],
                 "share_of_step": v["ms"] / sum(x["ms"] for x in prof.values()),
-                "avg_launch_ms": v["ms"] / v["launches"]}
+                "avg_launch_ms": v["ms"] / v["launches"],
+                "timing": "CUDA events around every launch of this kernel on the launching stream, eager pass of "
+                          "%d steps right after the timed region (the timed steps replay CUDA graphs)" % prof_steps}
     whole = pairs / world * GFLOP_PER_PAIR_FULL / (ms_max * 1e-3) / 1e3  # TFLOP/s per GPU, algorithmic
 
     cpu = None
@@ -335,7 +394,8 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": "BASELINE configs[1]: full inference (AE(y)+AE(x)+bpp+SI-Finder+SI-Net) on "
                                "batch %d of 320x1224 pairs per GPU, random-init KITTI_stereo_target_bpp0.02 shapes"
                                % B, "batch_per_gpu": B, "H": H, "W": W, "patch": [PH, PW],
-                   "l2": "3 rotating input batches; activations per step >> 126 MB L2", "parallelism": "dp%d" % world},
+                   "l2": "3 rotating input batches; activations per step >> 126 MB L2", "parallelism": "dp%d" % world,
+                   "timed_region": "K replays of the step's two CUDA graphs, inputs copied device-to-device"},
         "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms_max / args.steps},
         "gpu_launches": int(launches),
