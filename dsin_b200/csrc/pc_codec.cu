@@ -8,11 +8,15 @@
 // Parallel schedule.  The receptive field of the four masked (2,3,3) convolutions (probclass_imgcomp.py:150-176,
 // 214-261) reaches one step back per layer, so position p = (d, h, w) of every layer only needs positions whose
 // wavefront time 25 d + 5 h + w is smaller.  One CTA owns one stream = the depth slices d == stream (mod nstreams)
-// and walks a slice in steps of u = 5 h + w (<= 33 positions per step); per step: layer 0, 1, 2, logits, frequency
-// tables in parallel over (position, channel), then one thread runs the range coder over the step's symbols.
+// and walks a slice in steps of u = 5 h + w (<= 33 positions per step).  Inside the CTA the step is a two-stage
+// software pipeline (see pc_codec_kernel): a coder warp range-codes step u while nine bulk warps pre-accumulate
+// the taps of step u + 1 that are already old enough, then finish the chains and build the frequency tables.
 // Slice d may run u + 6 steps behind slice d - 1 (another CTA of the same image): a per-slice progress counter in
 // global memory (release / acquire) is the only inter-CTA synchronisation, so the slices of an image form a
 // software pipeline across its CTAs.  All CTAs of a launch must be co-resident (cooperative launch).
+// The encoder does not need the schedule at all (every symbol is known): run_codec() takes the full-volume path
+// (probclass.cu pc1_symbol_tables + pc_symbol_coder_kernel); the wavefront kernel in encode mode gives the same
+// bytes and is kept as a cross-check (DSIN_PC_ENCODE_WAVEFRONT=1).
 //
 // Determinism.  Every activation is an fmaf chain in the order of oracle/pc_codec.c (bias; live taps in raster
 // order; input channels ascending); exp is a fixed polynomial; only correctly rounded IEEE operations are used.
