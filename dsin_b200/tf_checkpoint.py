@@ -470,7 +470,9 @@ def read_checkpoint(prefix, names=None, verify=True):
         if sid not in shards:
             if not 0 <= sid < header["num_shards"]:
                 raise CheckpointError("%s lives in shard %d of %d" % (name, sid, header["num_shards"]))
-            shards[sid] = np.memmap(_data_path(prefix, sid, header["num_shards"]), dtype=np.uint8, mode="r")
+            path = _data_path(prefix, sid, header["num_shards"])
+            shards[sid] = np.memmap(path, dtype=np.uint8, mode="r") if os.path.getsize(path) > 0 \
+                else np.zeros(0, np.uint8)  # an empty shard (only zero-sized tensors) cannot be mapped
         blob = shards[sid]
         if e["offset"] < 0 or e["offset"] + e["size"] > blob.size:
             raise CheckpointError("%s runs past the end of its data shard" % name)
