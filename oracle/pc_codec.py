@@ -81,7 +81,7 @@ def encode(symbols_chw, W, nstreams=8, cap=None):
     sym = np.ascontiguousarray(symbols_chw, np.int32)
     arrs, centers = pack_weights(W)
     m = _model(sym.shape, arrs, centers)
-    cap = int(cap or (sym.size + 64))
+    cap = int(cap or (2 * sym.size + 64))  # a symbol costs at most 16 bits (every frequency is >= 1 of 65536)
     out = np.zeros((nstreams, cap), np.uint8)
     sizes = np.zeros(nstreams, np.int64)
     ideal = C.c_double(0.0)
