@@ -83,3 +83,60 @@ def test_oracle_codec_roundtrip_random_models(c, h, w, nstreams, seed, scale):
     assert np.array_equal(P.decode(streams, sym.shape, W), sym)
     total = 8 * sum(len(s) for s in streams)
     assert ideal - 32 * nstreams <= total <= ideal + 16 * nstreams + 8
+
+
+def _snappy_compress(data):
+    """A tiny greedy raw-Snappy encoder (literals + copies with 1-, 2- and 4-byte offsets) to feed the decoder."""
+    out = bytearray(T._put_varint(len(data)))
+    lit = bytearray()
+
+    def flush_literal():
+        i = 0
+        while i < len(lit):
+            chunk = lit[i:i + 70000]
+            n = len(chunk) - 1
+            if n < 60:
+                out.append(n << 2)
+            elif n < 256:
+                out.extend([60 << 2, n])
+            elif n < 65536:
+                out.extend([61 << 2]) or out.extend(n.to_bytes(2, "little"))
+            else:
+                out.extend([62 << 2]) or out.extend(n.to_bytes(3, "little"))
+            out.extend(chunk)
+            i += len(chunk)
+        lit.clear()
+
+    table, i = {}, 0
+    while i < len(data):
+        key = bytes(data[i:i + 4])
+        j = table.get(key) if len(key) == 4 else None
+        if len(key) == 4:
+            table[key] = i
+        if j is not None and i - j > 0:
+            ln = 4
+            while i + ln < len(data) and ln < 64 and data[j + ln] == data[i + ln]:  # may overlap: run-length style
+                ln += 1
+            off = i - j
+            flush_literal()
+            if 4 <= ln <= 11 and off < 2048:
+                out.extend([((off >> 8) << 5) | ((ln - 4) << 2) | 1, off & 0xFF])
+            elif off < 65536:
+                out.extend([((ln - 1) << 2) | 2]) or out.extend(off.to_bytes(2, "little"))
+            else:
+                out.extend([((ln - 1) << 2) | 3]) or out.extend(off.to_bytes(4, "little"))
+            i += ln
+        else:
+            lit.append(data[i])
+            i += 1
+    flush_literal()
+    return bytes(out)
+
+
+@settings(max_examples=80, deadline=None)
+@given(st.lists(st.one_of(st.binary(max_size=30), st.integers(1, 300).map(lambda n: b"ab" * n),
+                          st.integers(1, 400).map(lambda n: bytes([n % 251]) * n)), max_size=12))
+def test_snappy_decoder_inverts_a_real_encoder(parts):
+    data = b"".join(parts)
+    comp = _snappy_compress(data)
+    assert T.snappy_uncompress(comp) == data
