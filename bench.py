@@ -5,11 +5,15 @@
   python bench.py --impl reference ...                      the reference arithmetic on host cores
 
 A "step" is one AE.siNet_get_reconstructed-equivalent pass (AE(y), AE(x), bpp, SI-Finder, SI-Net;
-/root/reference/src/AE.py:132-148) over one batch of synthetic 320x1224 pairs.  N=1 workload =
-BASELINE.json configs[1] (batch 8, full inference).  `value` = Mpixels/s with inputs resident in
-HBM; `e2e` = the same through the public numpy call with pinned host buffers (H2D + D2H inside the
-timed region).  N>1: one process per GPU (torchrun), pairs sharded, one NCCL all-gather of per-rank
-metric partials; timing is the max over ranks.
+/root/reference/src/AE.py:132-148) over one batch of synthetic 320x1224 pairs.
+
+Default workload = BASELINE.json configs[4]: ONE global batch of 256 pairs per step, sharded over the N ranks with
+dist.shard_range (256 / 128 / 64 / 32 pairs per GPU at N = 1 / 2 / 4 / 8: strong scaling) and processed in
+micro-batches of 32 pairs -- at N = 1 this is north_star's "batch 32, 320x1224, 1xB200" operating point.
+`--batch B` instead fixes B pairs per GPU per step (weak scaling); `--batch 8` is configs[1].
+`value` = Mpixels/s with inputs resident in HBM; `e2e` = the same through the public numpy call on plain numpy
+uint8 arrays (pageable -> pinned staging, H2D and D2H all inside the timed region).  N>1: one process per GPU
+(torchrun), no data-path collective, one NCCL all-gather of per-rank metric partials; timing is the max over ranks.
 """
 from __future__ import annotations
 
@@ -26,13 +30,23 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, W = 320, 1224
-if os.environ.get("DSIN_BENCH_HW"):  # test hook only (tests/test_bench_contract.py): shrink the geometry
-    H, W = (int(v) for v in os.environ["DSIN_BENCH_HW"].split("x"))
+H, W = 320, 1224  # --hw HxW changes the geometry AND the metric / workload strings that name it
 PH, PW = 20, 24
-GFLOP_PER_PAIR_FULL = 1893.9  # SURVEY App. B / BASELINE.md section 4
+GFLOP_PER_PAIR_FULL = 1893.9  # SURVEY App. B / BASELINE.md section 4 (320x1224; scaled by area for other --hw)
 GFLOP_PER_PAIR_DECODE = 1640.0  # decode-side region: AE(y) + decoder(x) + SI-Finder + SI-Net
+GFLOP_PER_IMAGE_ENC_320x960 = 199.1  # configs[3]: encoder + quantiser + probclass
 METRIC = "Mpixels/s decode (320x1224 pairs)"
+
+
+def set_geometry(hw):
+    global H, W, METRIC, GFLOP_PER_PAIR_FULL, GFLOP_PER_PAIR_DECODE
+    h, w = (int(v) for v in hw.lower().split("x"))
+    if (h, w) != (H, W):
+        area = h * w / float(H * W)
+        GFLOP_PER_PAIR_FULL *= area      # approximation off the BASELINE geometry (the SI-Finder term is not linear)
+        GFLOP_PER_PAIR_DECODE *= area
+        H, W = h, w
+        METRIC = "Mpixels/s decode (%dx%d pairs; NOT the BASELINE geometry)" % (H, W)
 
 
 def log(*a):
@@ -193,7 +207,7 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def build_ae(device_index, residual_gamma=0.25):
+def build_ae(device_index, residual_gamma=0.25, precision=None):
     from dsin_b200 import config_parser, synth
     from dsin_b200.AE import AE
     from dsin_b200.decoder_imgcomp import decoder
@@ -205,7 +219,8 @@ def build_ae(device_index, residual_gamma=0.25):
     ae_config, _ = config_parser.parse(os.path.join(cfg, "ae_run_configs"))
     pc_config, _ = config_parser.parse(os.path.join(cfg, "pc_run_configs"))
     Wt = synth.make_weights(0, residual_gamma=residual_gamma)
-    return AE(ae_config, pc_config, encoder, decoder, siFinder, SI_full_img, siNet, cfg, weights=Wt)
+    ae_config.crop_size = (H, W)
+    return AE(ae_config, pc_config, encoder, decoder, siFinder, SI_full_img, siNet, cfg, weights=Wt, precision=precision)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -230,28 +245,36 @@ def run_ours(args, rank, world, local_rank):
             os.close(saved_fd)
     if rank != 0:
         g.build()  # no-op: rank 0 has built; this only loads/validates the library
-    from dsin_b200 import ops, synth
+    from dsin_b200 import ops, precision, synth
+    from dsin_b200.dist import gather_metrics, shard_range
     pk = peaks()
-    B = args.batch
-    ae = build_ae(local_rank)
+    ae = build_ae(local_rank, precision=args.precision)
     dev = torch.device("cuda", local_rank)
 
-    # three distinct input batches per rank, rotated: 3 x 2 x B x 4.7 MB, together with the
-    # activations (>= 16 x 12.5 MB per layer) far beyond the 126 MB L2
-    NSETS = 3
-    host_sets = []
-    for s in range(NSETS):
-        x, y = synth.make_batch(B, H, W, seed=1000 * (rank + 1) + 17 * s)
-        # host inputs are uint8 NCHW, as the reference's DataProvider delivers them (src/DataProvider.py:197-199)
-        px, py = ae.pinned_like(x.shape, np.uint8), ae.pinned_like(y.shape, np.uint8)
-        px.numpy()[...] = x.astype(np.uint8)
-        py.numpy()[...] = y.astype(np.uint8)
-        host_sets.append((px, py))
-    dev_sets = [(px.to(dev).float(), py.to(dev).float()) for px, py in host_sets]
+    # ---------------- which pairs this rank processes per step ----------------
+    if args.batch is not None:     # weak scaling: B pairs per GPU per step (configs[1] = --batch 8)
+        n_local, scaling, global_pairs = args.batch, "weak", args.batch * world
+        workload = ("BASELINE configs[1]-style: full inference on batch %d of %dx%d pairs per GPU per step"
+                    % (args.batch, H, W))
+    else:                          # strong scaling: one global batch, contiguous shards (configs[4])
+        lo, hi = shard_range(args.global_batch, rank, world)
+        n_local, scaling, global_pairs = hi - lo, "strong", args.global_batch
+        workload = ("BASELINE configs[4]: full inference on ONE global batch of %d %dx%d pairs per step, sharded "
+                    "contiguously over %d GPU(s) (dist.shard_range), micro-batches of %d pairs"
+                    % (args.global_batch, H, W, world, args.micro_batch))
+    MB = min(args.micro_batch, n_local)
+    micro = [MB] * (n_local // MB) + ([n_local % MB] if n_local % MB else [])
 
-    def step_device(i):
-        xd, yd = dev_sets[i % NSETS]
-        return ae.reconstruct_device(xd, yd)
+    # three distinct micro-batches of inputs per rank, rotated: with the activations of a micro-batch
+    # (>= 2 x MB x 12.5 MB per trunk layer) far beyond the 126 MB L2
+    NSETS = 3
+    host_np, dev_sets = [], []
+    for s in range(NSETS):
+        x, y = synth.make_batch(MB, H, W, seed=1000 * (rank + 1) + 17 * s)
+        # host inputs are plain numpy uint8 NCHW arrays, as the reference's DataProvider delivers them
+        # (src/DataProvider.py:197-199)
+        host_np.append((np.ascontiguousarray(x.astype(np.uint8)), np.ascontiguousarray(y.astype(np.uint8))))
+        dev_sets.append((torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -261,19 +284,26 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- device-resident timing ----------------
     # The timed steps replay the CUDA graphs the public call uses (inputs already in HBM, copied device-to-device
-    # into the captured input buffers): eager launching of ~230 kernels per step is host-bound when eight ranks
-    # share a busy host.  The per-kernel breakdown comes from a profiled eager pass right after the timed region.
-    step_device(0)  # first eager step also packs the weights; count the kernels of a steady-state step
-    l_step0 = ops.launch_count()
-    step_device(1)
-    launches_per_step = ops.launch_count() - l_step0
+    # into the captured input buffers): eager launching of ~230 kernels per micro-batch is host-bound when eight
+    # ranks share a busy host.  The per-kernel breakdown comes from a profiled eager pass after the timed region.
+    ae.reconstruct_device(dev_sets[0][0][:micro[0]], dev_sets[0][1][:micro[0]])  # packs the weights
+    l0 = ops.launch_count()
+    for j, m in enumerate(micro):
+        ae.reconstruct_device(dev_sets[j % NSETS][0][:m], dev_sets[j % NSETS][1][:m])
+    launches_per_step = ops.launch_count() - l0
 
-    def step_graph(i):
-        xd, yd = dev_sets[i % NSETS]
-        return ae.replay_device(xd, yd)
+    bits_parts = []
+
+    def step_graph(i, keep=False):
+        for j, m in enumerate(micro):
+            xd, yd = dev_sets[(i * len(micro) + j) % NSETS]
+            out = ae.replay_device(xd[:m], yd[:m])
+            if keep:
+                bits_parts.append(out["bits_sum"].clone())  # graph outputs are static buffers
+        return out
 
     for i in range(args.warmup):
-        out = step_graph(i)
+        step_graph(i)
     sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -281,70 +311,77 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
-    bits_total, npix_total = 0.0, 0
-    outs = []
     for i in range(args.steps):
-        out = step_graph(i)
-        outs.append(out["bits_sum"].clone())  # graph outputs are static buffers
+        step_graph(i, keep=True)
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
     launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
-    for bs in outs:
-        bits_total += float(bs.sum().item())
-        npix_total += B * H * W
+    bits_total = float(sum(float(b.sum().item()) for b in bits_parts))
+    npix_total = n_local * args.steps * H * W
+
     # profiled eager pass: CUDA events around every kernel call on the launching stream
-    prof_steps = min(args.steps, 3)
+    prof_mb = min(len(micro) * args.steps, 3)
     sync_all()
     ops.PROF.start()
-    for i in range(prof_steps):
-        step_device(i)
+    for j in range(prof_mb):
+        ae.reconstruct_device(dev_sets[j % NSETS][0][:micro[0]], dev_sets[j % NSETS][1][:micro[0]])
     torch.cuda.synchronize()
     ops.PROF.stop()
     prof = ops.PROF.summary()
+    prof_pairs = prof_mb * micro[0]
 
     # ---------------- decode-side region: receiver only, qbar(x) and y given ----------------
-    qb_sets = [ae.reconstruct_device(*dev_sets[s_])["qbar"].clone() for s_ in range(NSETS)]
-    qb_static, y_static = qb_sets[0].clone(), dev_sets[0][1].clone()
+    m0 = micro[0]
+    qb_sets = [ae.reconstruct_device(dev_sets[s_][0][:m0], dev_sets[s_][1][:m0])["qbar"].clone() for s_ in range(NSETS)]
+    qb_static, y_static = qb_sets[0].clone(), dev_sets[0][1][:m0].clone()
     for i in range(2):  # eager warm-up of the receiver path before capturing it
         ae.decode_side_device(qb_static, y_static)
     torch.cuda.synchronize()
     g_dec = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g_dec, capture_error_mode="thread_local"):
         ae.decode_side_device(qb_static, y_static)
+    dec_reps = max(1, min(len(micro) * args.steps, 8))
 
     def step_decode_side(i):
         qb_static.copy_(qb_sets[i % NSETS])
-        y_static.copy_(dev_sets[i % NSETS][1])
+        y_static.copy_(dev_sets[i % NSETS][1][:m0])
         g_dec.replay()
 
-    for i in range(min(2, args.warmup)):
+    for i in range(2):
         step_decode_side(i)
     d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     d0.record()
-    for i in range(args.steps):
+    for i in range(dec_reps):
         step_decode_side(i)
     d1.record()
     sync_all()
-    dec_ms = d0.elapsed_time(d1)
+    dec_ms_per_mb = d0.elapsed_time(d1) / dec_reps
 
-    # ---------------- end-to-end timing (public numpy API, pinned host buffers) ----------------
+    # ---------------- end-to-end timing (public numpy API, plain numpy uint8 arrays) ----------------
+    def step_e2e(i):
+        for j, m in enumerate(micro):
+            xn, yn = host_np[(i * len(micro) + j) % NSETS]
+            res = ae.siNet_get_reconstructed(xn[:m], yn[:m])
+        return res
+
     for i in range(min(2, args.warmup)):
-        ae.siNet_get_reconstructed(*host_sets[i % NSETS])
+        step_e2e(i)
     sync_all()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        y_dec, y_syn, x_dec, x_with_si, bpp = ae.siNet_get_reconstructed(*host_sets[i % NSETS])
+        y_dec, y_syn, x_dec, x_with_si, bpp = step_e2e(i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    h2d = 2 * B * 3 * H * W * 1  # uint8 images
-    d2h = 4 * B * 3 * H * W * 4 + 8 * B
+    h2d = 2 * n_local * 3 * H * W * 1  # uint8 images
+    d2h = 4 * n_local * 3 * H * W * 4 + 8 * n_local
 
-    # ---------------- quality metrics of the last batch (outside the timed regions) ----------------
+    # ---------------- quality metrics of the last micro-batch (outside the timed regions) ----------------
     last = ae.last
-    xs_nhwc = ops.nchw_to_nhwc(dev_sets[(args.steps - 1) % NSETS][0])
+    m_last = micro[-1]
+    xs_nhwc = ops.nchw_to_nhwc(dev_sets[((args.steps - 1) * len(micro) + len(micro) - 1) % NSETS][0][:m_last].contiguous())
     rec_nhwc = last["x_with_si"]._dsin_nhwc.clamp(0, 255) if hasattr(last.get("x_with_si"), "_dsin_nhwc") else None
     msssim_sum, msssim_n = 0.0, 0
     if rec_nhwc is not None:
@@ -352,10 +389,9 @@ def run_ours(args, rank, world, local_rank):
         msssim_sum, msssim_n = float(np.sum(msv)), int(msv.shape[0])
 
     # ---------------- reductions over ranks ----------------
-    t = torch.tensor([ms, e2e_s * 1e3, dec_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, dec_ms_per_mb], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    from dsin_b200.dist import gather_metrics
     gm = gather_metrics(bits_total, float(npix_total), msssim_sum, msssim_n, device=dev)  # the only collective
     ms_max, e2e_ms_max, dec_ms_max = float(t[0]), float(t[1]), float(t[2])
     if world > 1:
@@ -363,15 +399,20 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
     if rank != 0:
         return
-    pairs = B * args.steps * world
+    pairs = global_pairs * args.steps
     value = pairs * H * W * 1e-6 / (ms_max * 1e-3)
     e2e_value = pairs * H * W * 1e-6 / (e2e_ms_max * 1e-3)
+    dec_value = m0 * world * H * W * 1e-6 / (dec_ms_max * 1e-3)  # every rank runs the receiver micro-batch at once
 
     # ---------------- roofline of the dominant kernel ----------------
+    tot_prof_ms = sum(x["ms"] for x in prof.values())
     top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else None
-    kern = {k: {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] / prof_steps,
-                "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else None}
-            for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    kern = {}
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        tf = (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] else None
+        kern[k] = {"ms_per_pair": v["ms"] / prof_pairs, "launches": v["launches"] / prof_mb,
+                   "share": v["ms"] / tot_prof_ms, "tflops": tf,
+                   "frac_of_bf16_sustained": (tf / pk["tf_sust"]) if tf else None}
     roof = None
     if top is not None:
         name, v = top
@@ -387,10 +428,11 @@ def run_ours(args, rank, world, local_rank):
                 "frac": ach / pk["tf_sust"], "traffic": traffic,
                 "peak_source": pk["src"] + " bf16 dense sustained (fp16 shares the rate)",
                 "mma_terms_per_product": mma_terms, "frac_counting_issued_mma_work": mma_terms * ach / pk["tf_sust"],
-                "share_of_step": v["ms"] / sum(x["ms"] for x in prof.values()),
+                "share_of_step": v["ms"] / tot_prof_ms,
                 "avg_launch_ms": v["ms"] / v["launches"],
                 "timing": "CUDA events around every launch of this kernel on the launching stream, eager pass of "
-                          "%d steps right after the timed region (the timed steps replay CUDA graphs)" % prof_steps}
+                          "%d micro-batch(es) of %d pairs right after the timed region (the timed steps replay CUDA "
+                          "graphs)" % (prof_mb, micro[0])}
     whole = pairs / world * GFLOP_PER_PAIR_FULL / (ms_max * 1e-3) / 1e3  # TFLOP/s per GPU, algorithmic
 
     cpu = None
@@ -398,28 +440,31 @@ def run_ours(args, rank, world, local_rank):
         sec, cores = oracle_seconds_per_pair(1)
         model, _ = cpu_info()
         cpu = {"value": H * W * 1e-6 / sec, "unit": "Mpixels/s", "cores": cores, "kind": "port",
-               "sample": "1 pair 320x1224 full inference, oracle torch-CPU fp32 (%.1f s); CPU: %s" % (sec, model)}
+               "sample": "1 pair %dx%d full inference, oracle torch-CPU fp32 (%.1f s); CPU: %s" % (H, W, sec, model)}
 
     line = {
         "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": ae_dtype(), "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: full inference (AE(y)+AE(x)+bpp+SI-Finder+SI-Net) on "
-                               "batch %d of 320x1224 pairs per GPU, random-init KITTI_stereo_target_bpp0.02 shapes"
-                               % B, "batch_per_gpu": B, "H": H, "W": W, "patch": [PH, PW],
-                   "l2": "3 rotating input batches; activations per step >> 126 MB L2", "parallelism": "dp%d" % world,
-                   "timed_region": "K replays of the step's two CUDA graphs, inputs copied device-to-device"},
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": precision.dtype_string(ae.precision), "data": "synthetic",
+        "config": {"workload": workload + ", random-init KITTI_stereo_target_bpp0.02 shapes",
+                   "global_batch_per_step": global_pairs, "pairs_per_gpu_per_step": n_local, "micro_batches": micro,
+                   "H": H, "W": W, "patch": [PH, PW], "precision_policy": ae.precision.name,
+                   "l2": "3 rotating input micro-batches; activations per micro-batch >> 126 MB L2",
+                   "parallelism": "dp%d" % world,
+                   "timed_region": "K x (replays of the two CUDA graphs per micro-batch), inputs copied device-to-device"},
         "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms_max / args.steps},
+                "ms_per_step": e2e_ms_max / args.steps,
+                "inputs": "plain numpy uint8 arrays (pageable), staged through pinned buffers inside the timed call"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
         "regions": {
             "full": {"value": value, "unit": "Mpixels/s", "gflop_per_pair": GFLOP_PER_PAIR_FULL,
                      "what": "encode(x)+bpp + decode-side (the headline `value`)"},
-            "decode_side": {"value": pairs * H * W * 1e-6 / (dec_ms_max * 1e-3), "unit": "Mpixels/s",
-                            "ms_per_step": dec_ms_max / args.steps, "gflop_per_pair": GFLOP_PER_PAIR_DECODE,
-                            "tflops_per_gpu": pairs / world * GFLOP_PER_PAIR_DECODE / (dec_ms_max * 1e-3) / 1e3,
+            "decode_side": {"value": dec_value, "unit": "Mpixels/s",
+                            "ms_per_micro_batch": dec_ms_max, "micro_batch": m0, "gflop_per_pair": GFLOP_PER_PAIR_DECODE,
+                            "tflops_per_gpu": m0 * GFLOP_PER_PAIR_DECODE / (dec_ms_max * 1e-3) / 1e3,
+                            "frac_of_bf16_sustained": m0 * GFLOP_PER_PAIR_DECODE / (dec_ms_max * 1e-3) / 1e3 / pk["tf_sust"],
                             "what": "receiver only: AE(y)->y_dec, decoder(qbar_x), SI-Finder, SI-Net"}},
         "whole_path_tflops_per_gpu": whole,
         "whole_path_frac_of_bf16_sustained": whole / pk["tf_sust"],
@@ -479,6 +524,78 @@ def run_sif_only(args, rank, world, local_rank):
         "roofline": {"bound": "tensor", "kernel": "sif_match", "achieved": ach_match, "peak": pk["tf_sust"],
                      "unit": "TFLOP/s", "frac": ach_match / pk["tf_sust"], "traffic": None,
                      "peak_source": pk["src"] + " bf16 dense sustained", "whole_workload_tflops": ach},
+    }), flush=True)
+
+
+def run_enc_only(args, rank, world, local_rank):
+    """BASELINE configs[3]: encoder + quantiser + probability model (the sender's rate path: symbols and bpp) on
+    batch 64 of 320x960 crops, device-resident inputs; src/AE.py:50-53,85-87."""
+    import torch
+    import __graft_entry__ as g
+    torch.cuda.set_device(local_rank)
+    g.build()
+    if not args.hw:
+        set_geometry("320x960")
+    from dsin_b200 import ops, precision, synth
+    pk = peaks()
+    B = args.batch
+    ae = build_ae(local_rank, precision=args.precision)
+    pol = ae.precision
+    dev = torch.device("cuda", local_rank)
+    sets = []
+    for s in range(3):  # three rotating batches (3 x 64 x 3.7 MB fp32 inputs, activations >> L2)
+        x, _ = synth.make_batch(min(B, 8), H, W, seed=4000 + 31 * s)
+        reps = (B + x.shape[0] - 1) // x.shape[0]
+        sets.append(torch.from_numpy(np.concatenate([x] * reps)[:B]).to(dev))
+    pad = ae.pc_imgcomp.auto_pad_value(ae.ae_imgcomp)
+
+    def step(i):
+        z = ae.ae_imgcomp.encode(sets[i % 3], terms=pol.enc_x)
+        return ae.pc_imgcomp.bitcost(z.qbar, z.symbols, False, pad_value=pad, terms=pol.probclass)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ops.launch_count()
+    ops.PROF.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        bc = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ops.PROF.stop()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    prof = ops.PROF.summary()
+    if rank != 0:
+        return
+    gflop_img = GFLOP_PER_IMAGE_ENC_320x960 * (H * W) / (320.0 * 960.0)
+    whole = B * args.steps * gflop_img / (ms * 1e-3) / 1e3
+    name, v = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    ach = v["flops"] / (v["ms"] * 1e-3) / 1e12
+    terms = 3 if name.startswith("tc3_") else 1
+    tot = sum(x_["ms"] for x_ in prof.values())
+    print(json.dumps({
+        "metric": METRIC + " -- encoder + quantiser + probclass only", "value": B * args.steps * H * W * 1e-6 / (ms * 1e-3),
+        "unit": "Mpixels/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision.dtype_string(pol),
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[3]: encoder + quantiser + probclass bit cost, batch %d of %dx%d crops, "
+                               "device-resident inputs, eager launches" % (B, H, W), "batch_per_gpu": B,
+                   "precision_policy": pol.name, "l2": "3 rotating input batches; activations per step >> 126 MB L2"},
+        "gpu_launches": int(ops.launch_count() - l0), "clocks": clocks,
+        "bpp": float(bc._dsin_sum.sum().item()) / (B * H * W),
+        "whole_path_tflops": whole, "whole_path_frac_of_bf16_sustained": whole / pk["tf_sust"],
+        "roofline": {"bound": "tensor", "kernel": name, "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                     "frac": ach / pk["tf_sust"], "traffic": None, "mma_terms_per_product": terms,
+                     "frac_counting_issued_mma_work": terms * ach / pk["tf_sust"], "share_of_step": v["ms"] / tot,
+                     "avg_launch_ms": v["ms"] / v["launches"], "peak_source": pk["src"] + " bf16 dense sustained"},
+        "kernels": {k: {"ms_per_step": x_["ms"] / args.steps, "launches_per_step": x_["launches"] / args.steps,
+                        "tflops": (x_["flops"] / (x_["ms"] * 1e-3) / 1e12) if x_["flops"] else None}
+                    for k, x_ in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
     }), flush=True)
 
 
@@ -584,9 +701,9 @@ def run_roundtrip(args, rank, world, local_rank):
     }), flush=True)
 
 
-def ae_dtype():
-    from dsin_b200 import autoencoder_imgcomp
-    return getattr(autoencoder_imgcomp, "COMPUTE_DTYPE", "f32")
+def ae_dtype(policy=None):
+    from dsin_b200 import precision
+    return precision.dtype_string(policy)
 
 
 def main():
@@ -595,12 +712,20 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="pairs per GPU per step (weak scaling; 8 = BASELINE configs[1]); default: shard --global-batch")
+    ap.add_argument("--global-batch", type=int, default=256, help="pairs per step over all GPUs (configs[4])")
+    ap.add_argument("--micro-batch", type=int, default=32, help="pairs per device call")
+    ap.add_argument("--precision", default=None, help="precision policy name (dsin_b200/precision.py); default: shipped")
+    ap.add_argument("--hw", default=None, help="geometry HxW other than 320x1224 (the metric string then says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=8, help="range-coder streams per image (--workload codec)")
-    ap.add_argument("--workload", default="full", choices=["full", "sif", "codec", "roundtrip"],
-                    help="full = BASELINE configs[1]; sif = configs[2] (SI-Finder in isolation, use --batch 32)")
+    ap.add_argument("--workload", default="full", choices=["full", "sif", "enc", "codec", "roundtrip"],
+                    help="full = configs[4] / configs[1]; sif = configs[2] (SI-Finder in isolation, --batch 32); "
+                         "enc = configs[3] (encoder + quantiser + probclass on 320x960 crops, --batch 64)")
     args = ap.parse_args()
+    if args.hw:
+        set_geometry(args.hw)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -609,6 +734,11 @@ def main():
         run_reference(args, rank)
         return
     args.warmup = max(args.warmup, 3)
+    if args.workload != "full" and args.batch is None:
+        args.batch = {"sif": 32, "enc": 64}.get(args.workload, 8)
+    if args.workload == "enc":
+        run_enc_only(args, rank, world, local_rank)
+        return
     if args.workload == "sif":
         run_sif_only(args, rank, world, local_rank)
         return

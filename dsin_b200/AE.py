@@ -21,6 +21,7 @@ import torch
 from . import autoencoder_imgcomp as autoencoder
 from . import bits_imgcomp as bits
 from . import ops
+from . import precision as precision_policy
 from . import probclass_imgcomp as probclass
 from . import synth
 from . import tf_checkpoint
@@ -29,7 +30,7 @@ from .siFinder import GaussianPrior
 
 class AE(object):
     def __init__(self, ae_config, pc_config, encoder, decoder, siFinder, SI_full_img, siNet, cur_dir,
-                 weights=None, seed=0, device=None):
+                 weights=None, seed=0, device=None, precision=None):
         self.ae_config = ae_config
         self.pc_config = pc_config
         self._encode = encoder
@@ -54,8 +55,17 @@ class AE(object):
         if not getattr(self.ae_config, "heatmap", True):
             raise NotImplementedError("heatmap=False is not built")
 
-        ops.handle(device)  # fails loudly without libdsin_b200.so / an sm_100 GPU
-        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        # One process drives one GPU: the AE lives on torch's CURRENT device.  `device`, if given, must
+        # name that device -- every kernel is launched on the current device's stream and the C library rejects a
+        # handle whose device is not current.
+        cur = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        if device is not None and torch.device("cuda", device if isinstance(device, int) else
+                                               torch.device(device).index or 0).index != cur:
+            raise ValueError("AE(device=%r): call torch.cuda.set_device() first -- dsin_b200 runs one process per GPU "
+                             "on the current CUDA device (cuda:%d)" % (device, cur))
+        ops.handle(cur)  # fails loudly without libdsin_b200.so / an sm_100 GPU
+        self.device = torch.device("cuda", cur)
+        self.precision = precision_policy.get(precision)
         self.ae_imgcomp = autoencoder.get_network_cls(self.ae_config)(self.ae_config)
         self.pc_imgcomp = probclass.get_network_cls(self.pc_config)(self.pc_config,
                                                                     num_centers=self.ae_config.num_centers)
@@ -68,7 +78,8 @@ class AE(object):
         self.last = {}
         # CUDA graphs for the numpy entry points: one capture per input shape, replayed afterwards, so a call
         # costs two graph launches instead of ~230 kernel launches (batch 1 is launch-bound otherwise)
-        self.use_cuda_graph = os.environ.get("DSIN_CUDA_GRAPH", "1") != "0"
+        self.use_cuda_graph = True  # set to False for eager launches (tests compare the two)
+        self.e2e_overlap = True     # copy y_dec/x_dec out on a side stream while the SI-Finder / SI-Net run
         self._graphs = {}
 
     # ------------------------------------------------------------------ weights
@@ -96,9 +107,12 @@ class AE(object):
         """The variables `load_model` of the reference restores for inference (src/AE.py:158-172): scopes
         encoder/encoder_body, decoder, imgcomp and -- unless AE_only -- siNetwork.  Optimizer slots and the
         training step of a training checkpoint are ignored."""
-        names = [k for k in synth.variable_names(self.ae_config.arch_param_B) if
+        c = self.ae_config
+        with_si = (not self.AE_only) and (getattr(c, "load_train_step", False) or
+                                          (getattr(c, "test_model", True) and not getattr(c, "train_model", False)))
+        names = [k for k in synth.variable_names(c.arch_param_B) if
                  k.startswith(("encoder/encoder_body/", "decoder/", "imgcomp/"))
-                 or (not self.AE_only and k.startswith("siNetwork/"))]
+                 or (with_si and k.startswith("siNetwork/"))]
         return names
 
     def load_model(self, load_path):
@@ -113,6 +127,12 @@ class AE(object):
             W = synth.load_weights(npz)
         else:
             raise FileNotFoundError("neither {}.index (TF-V2 checkpoint) nor {} found".format(load_path, npz))
+        if not self.AE_only and not any(k.startswith("siNetwork/") for k in W):
+            # "train SI for the first time from an AE checkpoint" (src/AE.py:163-172): the reference restores the
+            # AE scopes only and keeps the SI-Net's initialiser values
+            for k, v in self.weights.items():
+                if k.startswith("siNetwork/"):
+                    W[k] = v
         self.set_weights(W)
 
     # ------------------------------------------------------------------ helpers kept from the reference
@@ -182,13 +202,27 @@ class AE(object):
     def _encode_decode(self, x, y):
         """AE(y) and AE(x) as one batch of 2B images (src/AE.py:50-57,150-152) + bit cost of x (src/AE.py:85-87)."""
         B = x.shape[0]
-        both = torch.cat([y, x], dim=0)
-        z = self._encode(both, self.ae_imgcomp, is_training=False)
-        dec = self._decode(z.qbar, self.ae_imgcomp, is_training=False)
-        qx, sx = z.qbar[B:], z.symbols[B:]
+        P = self.precision
+        if P.enc_x == P.enc_y:
+            z = self._encode(torch.cat([y, x], dim=0), self.ae_imgcomp, is_training=False, terms=P.enc_x)
+            qall, qx, sx = z.qbar, z.qbar[B:], z.symbols[B:]
+        else:  # the two encoder passes run at different operand precision: two launches per layer
+            zy = self._encode(y, self.ae_imgcomp, is_training=False, terms=P.enc_y)
+            zx = self._encode(x, self.ae_imgcomp, is_training=False, terms=P.enc_x)
+            qall, qx, sx = self._cat_qbar(zy.qbar, zx.qbar), zx.qbar, zx.symbols
+        dec = self._decode(qall, self.ae_imgcomp, is_training=False, terms=P.dec)
         bc = self.pc_imgcomp.bitcost(qx, sx, is_training=False,
-                                     pad_value=self.pc_imgcomp.auto_pad_value(self.ae_imgcomp))
+                                     pad_value=self.pc_imgcomp.auto_pad_value(self.ae_imgcomp), terms=P.probclass)
         return {"dec": dec, "symbols": sx, "qbar": qx, "bits": bc, "bits_sum": bc._dsin_sum}
+
+    @staticmethod
+    def _cat_qbar(qa, qb):
+        """Concatenate two bottlenecks along the batch, keeping the NHWC twin the decoder consumes."""
+        q = torch.cat([qa, qb], dim=0)
+        na, nb = getattr(qa, "_dsin_nhwc", None), getattr(qb, "_dsin_nhwc", None)
+        if na is not None and nb is not None:
+            q._dsin_nhwc = torch.cat([na, nb], dim=0)
+        return q
 
     def replay_device(self, x, y):
         """reconstruct_device through the captured CUDA graphs: x, y (B,3,H,W) CUDA tensors (any dtype) are copied
@@ -233,8 +267,9 @@ class AE(object):
         bitstream carries) and the side image y -> AE(y) (src/AE.py:150-152), decoder(x) (src/AE.py:57),
         SI-Finder and SI-Net (src/AE.py:60-69).  No encoder pass over x and no probability model."""
         B = y.shape[0]
-        zy = self._encode(y, self.ae_imgcomp, is_training=False)
-        dec = self._decode(torch.cat([zy.qbar, qbar_x], dim=0), self.ae_imgcomp, is_training=False)
+        zy = self._encode(y, self.ae_imgcomp, is_training=False, terms=self.precision.enc_y)
+        dec = self._decode(torch.cat([zy.qbar, qbar_x], dim=0), self.ae_imgcomp, is_training=False,
+                           terms=self.precision.dec)
         return self._side_information(dec, y, B)
 
     def _side_information(self, dec, y, B):
@@ -250,7 +285,7 @@ class AE(object):
             x_dec, y, self.mask, self._y_patch_h, self._y_patch_w, self.ae_config, y_dec)
         fused = getattr(self._siNet, "fused", None)
         if fused is not None and hasattr(y_syn, "_dsin_nhwc"):
-            x_with_si = fused(x_dec._dsin_nhwc, y_syn._dsin_nhwc)
+            x_with_si = fused(x_dec._dsin_nhwc, y_syn._dsin_nhwc, terms=self.precision.sinet)
         else:  # generic callable: normalise/concat/denormalise with torch elementwise ops
             mean, var = self.get_mean_var()
             m = torch.from_numpy(mean).to(y.device)
@@ -274,9 +309,8 @@ class AE(object):
         src/DataProvider.py:197-199) or float32 holding uint8 values.  Returns numpy
         (y_dec, y_syn, x_dec, x_with_si, bpp) like src/AE.py:148.  The returned arrays are views of
         pinned staging buffers that are recycled two calls later.  The copy-out of y_dec/x_dec runs on
-        a side stream while the SI-Finder and SI-Net are still computing.  With `use_cuda_graph` (default;
-        DSIN_CUDA_GRAPH=0 disables) the step is replayed from two CUDA graphs captured on the first call
-        with this input shape."""
+        a side stream while the SI-Finder and SI-Net are still computing.  With `use_cuda_graph` (default) the step is replayed from two CUDA graphs captured on the first call
+        with this input shape (`use_cuda_graph = False` launches eagerly)."""
         xs, ys = self._stage(x, "x"), self._stage(y, "y")
         self._ring ^= 1
         main = torch.cuda.current_stream()
@@ -285,7 +319,7 @@ class AE(object):
         B = xs.shape[0]
         early = {}
 
-        overlap = os.environ.get("DSIN_E2E_OVERLAP", "1") != "0"
+        overlap = self.e2e_overlap
 
         def on_decoded(dec):
             buf = self._pinned_out("dec", dec.shape, dec.dtype)
@@ -334,7 +368,7 @@ class AE(object):
         (the coder src/probclass_imgcomp.py:361-482 prepares for); 8 * len(bitstream) / (H * W) is the real bpp
         that `bpp` of siNet_get_reconstructed estimates."""
         xd = self._to_device(x, "x")
-        z = self._encode(xd, self.ae_imgcomp, is_training=False)
+        z = self._encode(xd, self.ae_imgcomp, is_training=False, terms=self.precision.enc_x)
         self.last = {"symbols": z.symbols, "qbar": z.qbar}
         return self.pc_imgcomp.encode_symbols(z.symbols, self.ae_imgcomp._centers, nstreams=nstreams)
 
@@ -354,6 +388,6 @@ class AE(object):
 
     def create_y_dec(self, y):
         yd = self._to_device(y, "y")
-        z = self._encode(yd, self.ae_imgcomp, is_training=False)
-        dec = self._decode(z.qbar, self.ae_imgcomp, is_training=False)
+        z = self._encode(yd, self.ae_imgcomp, is_training=False, terms=self.precision.enc_y)
+        dec = self._decode(z.qbar, self.ae_imgcomp, is_training=False, terms=self.precision.dec)
         return self._to_host([dec])[0]

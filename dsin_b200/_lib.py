@@ -49,7 +49,7 @@ SIGNATURES = {
     "dsin_conv2d_tc": (_I, [_P, C.POINTER(ConvDesc), _I] + [_P] * 14),
     "dsin_f32_to_split": (_I, [_P, _P, _P, _P, _I64, _P]),
     "dsin_split_to_f32": (_I, [_P, _P, _P, _P, _I64, _P]),
-    "dsin_heatmap_quantize": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "dsin_heatmap_quantize": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "dsin_probclass_workspace_bytes": (_I64, [_I, _I, _I, _I, _I]),
     "dsin_probclass_bits": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, C.c_float] + [_P] * 8 + [_P, _P, _P, _P]),
     "dsin_probclass_tc_workspace_bytes": (_I64, [_I, _I, _I, _I]),
@@ -62,6 +62,7 @@ SIGNATURES = {
     "dsin_sif_gather": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "dsin_pc_codec_workspace_bytes": (_I64, [_I, _I, _I, _I]),
     "dsin_pc_encode": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _I64, _P, _P, _P, _P]),
+    "dsin_pc_encode_wavefront": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _I64, _P, _P, _P, _P]),
     "dsin_pc_decode": (_I, [_P, _P, _I64, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P]),
 }
 

@@ -8,7 +8,6 @@ BatchNorm is folded to a per-channel scale/shift at weight-load time.
 """
 from __future__ import annotations
 
-import os
 from collections import namedtuple
 
 import numpy as np
@@ -21,14 +20,9 @@ EncoderOutput = namedtuple("EncoderOutput", ["qbar", "qhard", "symbols", "z", "h
 BN_EPS = np.float32(1e-5)
 arch_param_n = 128
 
-# How the 64 trunk convs (3x3, 128->128) run:
-#   "tc3"  tcgen05, split-fp16 operands, 3 MMAs per product (fp32-class; the parity mode)
-#   "tc1"  tcgen05, fp16 operands, 1 MMA (fast mode; symbols no longer bit-exact)
-#   "simt" CUDA-core fp32 (v1 kernel, kept as the on-GPU cross-check)
-TRUNK_MODE = os.environ.get("DSIN_TRUNK_MODE", "tc3")
-H1_S2D = os.environ.get("DSIN_H1_S2D", "1") != "0"    # h1 as space-to-depth + 3x3 tensor-core conv
-H13_D2S = os.environ.get("DSIN_H13_D2S", "1") != "0"  # h13 as one 3x3 conv + depth-to-space (else 4 phases)
-COMPUTE_DTYPE = "f16x2-split tensor-core (fp32 accumulate) + f32 CUDA-core"
+# Every conv of the encoder/decoder runs on tcgen05 (csrc/conv_tc*.cu).  `terms` (precision.py) says how many MMAs
+# build one product: 3 = split-fp16 hi*hi + hi*lo + lo*hi (fp32-class), 1 = fp16 operands.  There is no other
+# backend: an image whose quarter-resolution trunk is smaller than one 16x32 tile block is rejected.
 
 
 def get_network_cls(config):
@@ -114,15 +108,15 @@ class _Network(object):
     def load_weights(self, W):
         raise NotImplementedError()
 
-    def encode(self, x, is_training=False):
+    def encode(self, x, is_training=False, terms=3):
         if is_training is True:
             raise NotImplementedError("dsin_b200 implements the inference path only")
-        return self._encode(x)
+        return self._encode(x, terms)
 
-    def decode(self, q, is_training=False):
+    def decode(self, q, is_training=False, terms=3):
         if is_training is True:
             raise NotImplementedError("dsin_b200 implements the inference path only")
-        return self._decode(q)
+        return self._decode(q, terms)
 
 
 class _CVPR(_Network):
@@ -164,16 +158,14 @@ class _CVPR(_Network):
         return t
 
     @staticmethod
-    def _terms():
-        return 3 if TRUNK_MODE == "tc3" else 1
+    def _require_tileable(hh, ww):
+        """All tcgen05 layers tile 8x16 pixel blocks (16x32 input pixels for the stride-2 layers)."""
+        if hh < 16 or ww < 32 or hh % 2 or ww % 2:
+            raise ValueError("dsin_b200: images must be at least 64x128 with sides divisible by 8 "
+                             "(quarter-resolution trunk %dx%d); there is no non-tensor-core path" % (hh, ww))
 
-    def _tc_usable(self, hh, ww):
-        """All tcgen05 layers tile 8x16 pixel blocks (16x32 input pixels for stride 2)."""
-        return TRUNK_MODE in ("tc3", "tc1") and hh >= 16 and ww >= 32
-
-    def _trunk_tc(self, cur, pre, blk, fin):
+    def _trunk_tc(self, cur, pre, blk, fin, terms):
         """cur: split-fp16 pair.  15 residual blocks + final block, 3 skip levels."""
-        terms = self._terms()
         r0 = cur
         for b in range(self.config.arch_param_B):
             rb = cur
@@ -184,78 +176,45 @@ class _CVPR(_Network):
         t = ops.conv_tc(cur, self._tc(pre + fin + "/conv1"), terms=terms)
         return ops.conv_tc(t, self._tc(pre + fin + "/conv2"), res1=cur, res2=r0, terms=terms)
 
-    def _encode_tc(self, x):
-        L, E, terms = self.layers, synth.ENC, self._terms()
-        if H1_S2D and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
-            if self._h1_tc is None:
-                self._h1_tc = ops.ConvTC(self._h1_s2d)
-            cur = ops.conv_tc(ops.nchw_to_s2d_split32(x), self._h1_tc, terms=terms,
-                              prof=("tc%d_conv5x5_3to64_s2_as3x3", 2.0 * x.shape[0] * (x.shape[2] // 2)
-                                    * (x.shape[3] // 2) * 25 * 3 * 64))
-        else:
-            net = ops.nchw_to_nhwc(x, normalize=True)
-            net = ops.conv2d(net, L[E + "h1"])  # cin = 3 on CUDA cores
-            cur = ops.f32_to_split(net)
+    def _encode_tc(self, x, terms):
+        E = synth.ENC
+        if self._h1_tc is None:
+            self._h1_tc = ops.ConvTC(self._h1_s2d)
+        cur = ops.conv_tc(ops.nchw_to_s2d_split32(x, with_lo=terms == 3), self._h1_tc, terms=terms,
+                          prof=("tc%d_conv5x5_3to64_s2_as3x3", 2.0 * x.shape[0] * (x.shape[2] // 2)
+                                * (x.shape[3] // 2) * 25 * 3 * 64))
         cur = ops.conv_tc(cur, self._tc(E + "h2"), terms=terms)
-        cur = self._trunk_tc(cur, E, "res_block_enc_%d/enc_%d_%d", "res_block_enc_final")
+        cur = self._trunk_tc(cur, E, "res_block_enc_%d/enc_%d_%d", "res_block_enc_final", terms)
         return ops.conv_tc(cur, self._tc(E + "to_bn"), terms=terms, out_f32=True)
 
-    def _decode_tc(self, q_nhwc):
-        D, terms = synth.DEC, self._terms()
-        cur = ops.f32_to_split(q_nhwc)
+    def _decode_tc(self, q_nhwc, terms):
+        D = synth.DEC
+        cur = ops.f32_to_split(q_nhwc, with_lo=terms == 3)
         cur = ops.conv_tc(cur, self._tc(D + "from_bn"), terms=terms)
-        cur = self._trunk_tc(cur, D, "res_block_dec_%d/dec_%d_%d", "dec_after_res")
+        cur = self._trunk_tc(cur, D, "res_block_dec_%d/dec_%d_%d", "dec_after_res", terms)
         cur = ops.conv_tc(cur, self._tc(D + "h12"), terms=terms)
-        if H13_D2S:
-            if self._h13_tc is None:
-                self._h13_tc = ops.ConvTC(self._h13_d2s)
-            return ops.conv_tc(cur, self._h13_tc, terms=terms, out_f32=True,  # BN, denormalise, clip, depth-to-space
-                               prof=("tc%d_conv5x5_64to3_T_as3x3", 2.0 * cur[0].shape[0] * cur[0].shape[1]
-                                     * cur[0].shape[2] * 25 * 64 * 3))
-        return ops.conv_tc(cur, self._tc(D + "h13"), terms=terms, out_f32=True)  # BN, denormalise, clip fused
+        if self._h13_tc is None:
+            self._h13_tc = ops.ConvTC(self._h13_d2s)
+        return ops.conv_tc(cur, self._h13_tc, terms=terms, out_f32=True,  # BN, denormalise, clip, depth-to-space
+                           prof=("tc%d_conv5x5_64to3_T_as3x3", 2.0 * cur[0].shape[0] * cur[0].shape[1]
+                                 * cur[0].shape[2] * 25 * 64 * 3))
 
-    # -- CUDA-core fp32 path (v1 kernels; on-GPU cross-check and small-image fallback) -------------
-    def _trunk(self, net, pre, blk, fin):
-        L = self.layers
-        r0 = net
-        for b in range(self.config.arch_param_B):
-            rb = net
-            for i in (1, 2, 3):
-                sc = pre + blk % (b, b, i)
-                t = ops.conv2d(net, L[sc + "/conv1"])
-                # conv2 + BN, + block input, and (+ group input after the third block)
-                net = ops.conv2d(t, L[sc + "/conv2"], res1=net, res2=rb if i == 3 else None)
-        t = ops.conv2d(net, L[pre + fin + "/conv1"])
-        return ops.conv2d(t, L[pre + fin + "/conv2"], res1=net, res2=r0)
-
-    def _encode(self, x):
-        """x: (N,3,H,W) fp32 CUDA tensor, uint8-valued."""
-        L, E = self.layers, synth.ENC
-        if self._tc_usable(x.shape[2] // 4, x.shape[3] // 4):
-            z33 = self._encode_tc(x)
-        else:
-            net = ops.nchw_to_nhwc(x, normalize=True)
-            net = ops.conv2d(net, L[E + "h1"])
-            net = ops.conv2d(net, L[E + "h2"])
-            net = self._trunk(net, E, "res_block_enc_%d/enc_%d_%d", "res_block_enc_final")
-            z33 = ops.conv2d(net, L[E + "to_bn"])
-        qbar_nhwc, qbar_nchw, symbols = ops.heatmap_quantize(z33, self._centers)
+    def _encode(self, x, terms=3):
+        """x: (N,3,H,W) fp32 CUDA tensor, uint8-valued -> EncoderOutput(qbar, qhard, symbols, z, heatmap), all
+        (N,C,h,w) like the reference's (src/autoencoder_imgcomp.py:239-245)."""
+        self._require_tileable(x.shape[2] // 4, x.shape[3] // 4)
+        z33 = self._encode_tc(x, terms)
+        qbar_nhwc, qbar_nchw, symbols, qhard, z, heatmap = ops.heatmap_quantize(z33, self._centers, full=True)
         qbar_nchw._dsin_nhwc = qbar_nhwc
-        return EncoderOutput(qbar_nchw, None, symbols, None, None)
+        return EncoderOutput(qbar_nchw, qhard, symbols, z, heatmap)
 
-    def _decode(self, q):
+    def _decode(self, q, terms=3):
         """q: qbar (N,C,h,w); returns x_dec (N,3,H,W) clipped to [0,255]."""
-        L, D = self.layers, synth.DEC
         q_nhwc = getattr(q, "_dsin_nhwc", None)
         if q_nhwc is None:
             q_nhwc = ops.nchw_to_nhwc(q.contiguous(), normalize=False)
-        if self._tc_usable(2 * q.shape[2], 2 * q.shape[3]):
-            img_nhwc = self._decode_tc(q_nhwc)
-        else:
-            net = ops.conv2d(q_nhwc, L[D + "from_bn"])
-            net = self._trunk(net, D, "res_block_dec_%d/dec_%d_%d", "dec_after_res")
-            net = ops.conv2d(net, L[D + "h12"])
-            img_nhwc = ops.conv2d(net, L[D + "h13"])  # BN, denormalise, clip fused
+        self._require_tileable(2 * q.shape[2], 2 * q.shape[3])
+        img_nhwc = self._decode_tc(q_nhwc, terms)
         out = ops.nhwc_to_nchw(img_nhwc)
         out._dsin_nhwc = img_nhwc
         return out

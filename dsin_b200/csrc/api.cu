@@ -9,7 +9,9 @@ int dsin_create(dsin_handle_t* out, int device) {
   if (!out) return DSIN_ERR_ARG;
   *out = nullptr;
   int count = 0;
-  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return DSIN_ERR_CUDA;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count ||
+      device >= DSIN_MAX_DEVICES)
+    return DSIN_ERR_CUDA;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DSIN_ERR_CUDA;
   if (prop.major != 10) return DSIN_ERR_UNSUPPORTED;  // sm_100a only: no fallback path exists

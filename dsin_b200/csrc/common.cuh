@@ -21,8 +21,19 @@ static inline int dsin_fail(dsin_handle_t h, int code, const char* fmt, const ch
   return code;
 }
 
+#define DSIN_MAX_DEVICES 64
+
+// A handle belongs to one device; every entry point must be called with that device current (its launches,
+// tensor maps and per-device kernel attributes all assume it).
+static inline bool dsin_device_is_current(dsin_handle_t h) {
+  int dev = -1;
+  return h && cudaGetDevice(&dev) == cudaSuccess && dev == h->device;
+}
+
 #define DSIN_REQUIRE(h, cond, msg)                                        \
   do {                                                                    \
+    if (!dsin_device_is_current(h))                                       \
+      return dsin_fail((h), DSIN_ERR_ARG, "%s: the handle's device is not the current CUDA device", __func__); \
     if (!(cond)) return dsin_fail((h), DSIN_ERR_ARG, "%s: " msg, __func__); \
   } while (0)
 

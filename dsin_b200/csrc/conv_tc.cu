@@ -19,7 +19,6 @@
 //   terms = 1:  hi*hi only             -> fp16 operands (fast mode)
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
 // warps 2-5 = epilogue (TMEM -> registers -> scale/shift/act/residual/post -> global).
-#include <stdlib.h>
 #include "tc_common.cuh"
 #include "conv_tc.cuh"
 
@@ -383,12 +382,12 @@ template <int KC, int NPAD, int TERMS, bool PS = false>
 int launch_one(dsin_handle_t h, const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh,
                const CUtensorMap& wl, const GP& p, cudaStream_t st) {
   using C = Cfg<KC, NPAD, TERMS, PS>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[DSIN_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
+  if (!configured[h->device]) {
     if (cudaFuncSetAttribute(conv_tc_kernel<KC, NPAD, TERMS, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              C::kSmem) != cudaSuccess)
       return dsin_fail(h, DSIN_ERR_CUDA, "%s: cannot raise dynamic shared memory", __func__);
-    configured = true;
+    configured[h->device] = true;
   }
   int grid = p.total_tiles < h->sm_count ? p.total_tiles : h->sm_count;
   conv_tc_kernel<KC, NPAD, TERMS, PS><<<grid, 192, C::kSmem, st>>>(xh, xl, wh, wl, p);
@@ -549,7 +548,19 @@ extern "C" int dsin_conv2d_tc(dsin_handle_t h, const dsin_conv_desc_t* d, int te
       }
     p.tiles_w = (p.GW + BW - 1) / BW; p.tiles_h = (p.GH + BH - 1) / BH;
     p.total_tiles = d->n * p.tiles_w * p.tiles_h;
-    static const bool use_pairs = getenv("DSIN_NO_CTA2") == nullptr;
+    const bool use_pairs = (d->flags & DSIN_CONV_NO_CTA_PAIR) == 0;
+    if (use_pairs && terms == 1 && !(d->flags & DSIN_CONV_NO_WEIGHT_STATIONARY) && k == 3 && d->stride == 1 &&
+        d->dilation == 1 && dil_x == 1 && d->cin == 128 && d->cout == 128 && y_hi && !y_lo && !y_f32 && !res1_lo &&
+        !res2_lo && d->post == DSIN_POST_NONE && d->act != DSIN_ACT_LRELU02 && p.total_tiles >= 2) {
+      // fp16-operand trunk layer: weight-stationary kernel with a halo-resident activation tile (conv_ws.cu)
+      ConvWsArgs a;
+      memset(&a, 0, sizeof(a));
+      a.scale = scale; a.shift = shift;
+      a.r1 = p.r1h; a.r2 = p.r2h; a.y = p.yh;
+      a.n = d->n; a.OH = p.OH; a.OW = p.OW; a.act = d->act;
+      a.base_offset_mode = (d->flags & DSIN_CONV_WS_NO_BASE_OFFSET) ? 0 : 1;
+      return conv_ws_launch(h, (const __half*)x_hi, (const __half*)w_hi, a, st);
+    }
     if (use_pairs && KC == 64 && NPAD == 128 && d->cout == 128 && y_hi && !y_f32 && d->post == DSIN_POST_NONE &&
         d->act != DSIN_ACT_LRELU02 && p.total_tiles >= 2) {
       // CTA-pair kernel: each CTA of a pair loads half of the weight slab (64 couts)

@@ -37,3 +37,15 @@ struct ConvTc2Res {  // TMA maps of the residual planes (r1 hi, r1 lo, r2 hi, r2
 };
 int conv_tc2_launch(dsin_handle_t h, int terms, const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh,
                     const CUtensorMap& wl, const ConvTc2Args& p, cudaStream_t st);
+
+// Weight-stationary, halo-tile CTA-pair kernel for the fp16-operand (terms = 1) 3x3 128->128 layers (conv_ws.cu).
+struct ConvWsArgs {
+  const float* scale;
+  const float* shift;
+  const __half *r1, *r2;  // optional residual tensors (fp16 NHWC, same shape as y)
+  __half* y;
+  int n, OH, OW, act;
+  int tiles_w, tiles_h, total_tiles;  // filled by conv_ws_launch
+  int base_offset_mode;               // 1: the tap's column shift is declared in the descriptor's base-offset field
+};
+int conv_ws_launch(dsin_handle_t h, const __half* x, const __half* w_packed, const ConvWsArgs& a, cudaStream_t st);

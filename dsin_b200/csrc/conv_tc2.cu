@@ -282,12 +282,12 @@ template <int TERMS>
 int launch2(dsin_handle_t h, const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh,
             const CUtensorMap& wl, const ConvTc2Res& rm, const ConvTc2Args& p, cudaStream_t st) {
   using C = Cfg2<TERMS>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[DSIN_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
+  if (!configured[h->device]) {
     if (cudaFuncSetAttribute(conv_tc2_kernel<TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem) !=
         cudaSuccess)
       return dsin_fail(h, DSIN_ERR_CUDA, "%s: cannot raise dynamic shared memory", __func__);
-    configured = true;
+    configured[h->device] = true;
   }
   const int pairs = (p.total_tiles + 1) / 2;
   int clusters = h->sm_count / 2;

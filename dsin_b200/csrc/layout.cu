@@ -55,7 +55,7 @@ __global__ void concat_normalize_split32_kernel(const float* __restrict__ a, con
     }
   }
   reinterpret_cast<uint4*>(hi)[idx] = *reinterpret_cast<const uint4*>(h);
-  reinterpret_cast<uint4*>(lo)[idx] = *reinterpret_cast<const uint4*>(l);
+  if (lo) reinterpret_cast<uint4*>(lo)[idx] = *reinterpret_cast<const uint4*>(l);
 }
 
 // NCHW image -> normalised, space-to-depth(2) NHWC split-fp16 with 32 channels: out[n, a, b, (sy*2+sx)*3 + c] =
@@ -86,7 +86,7 @@ __global__ void nchw_to_s2d_split32_kernel(const float* __restrict__ x, __half* 
     l[e] = __float2half_rn(v - __half2float(h[e]));
   }
   reinterpret_cast<uint4*>(hi)[idx] = *reinterpret_cast<const uint4*>(h);
-  reinterpret_cast<uint4*>(lo)[idx] = *reinterpret_cast<const uint4*>(l);
+  if (lo) reinterpret_cast<uint4*>(lo)[idx] = *reinterpret_cast<const uint4*>(l);
 }
 
 __global__ void f32_to_split_kernel(const float* __restrict__ x, __half* __restrict__ hi,
@@ -96,14 +96,14 @@ __global__ void f32_to_split_kernel(const float* __restrict__ x, __half* __restr
   float v = x[i];
   __half h = __float2half_rn(v);
   hi[i] = h;
-  lo[i] = __float2half_rn(v - __half2float(h));
+  if (lo) lo[i] = __float2half_rn(v - __half2float(h));
 }
 
 __global__ void split_to_f32_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
                                     float* __restrict__ y, int64_t count) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  y[i] = __half2float(hi[i]) + __half2float(lo[i]);
+  y[i] = lo ? __half2float(hi[i]) + __half2float(lo[i]) : __half2float(hi[i]);
 }
 
 extern "C" {
@@ -139,7 +139,7 @@ int dsin_concat_normalize(dsin_handle_t h, const float* a, const float* b, float
 
 int dsin_concat_normalize_split32(dsin_handle_t h, const float* a, const float* b, uint16_t* hi, uint16_t* lo, int n,
                                   int hh, int ww, void* stream) {
-  DSIN_REQUIRE(h, a && b && hi && lo && n > 0, "bad argument");
+  DSIN_REQUIRE(h, a && b && hi && n > 0, "bad argument");
   int64_t tot = (int64_t)n * hh * ww;
   concat_normalize_split32_kernel<<<(unsigned)((tot * 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       a, b, (__half*)hi, (__half*)lo, tot);
@@ -149,7 +149,7 @@ int dsin_concat_normalize_split32(dsin_handle_t h, const float* a, const float* 
 
 int dsin_nchw_to_s2d_split32(dsin_handle_t h, const float* x_nchw, uint16_t* hi, uint16_t* lo, int n, int hh, int ww,
                              void* stream) {
-  DSIN_REQUIRE(h, x_nchw && hi && lo && n > 0 && hh % 2 == 0 && ww % 2 == 0, "bad argument");
+  DSIN_REQUIRE(h, x_nchw && hi && n > 0 && hh % 2 == 0 && ww % 2 == 0, "bad argument");
   int64_t tot = (int64_t)n * (hh / 2) * (ww / 2) * 4;
   nchw_to_s2d_split32_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       x_nchw, (__half*)hi, (__half*)lo, n, hh, ww);
@@ -159,7 +159,7 @@ int dsin_nchw_to_s2d_split32(dsin_handle_t h, const float* x_nchw, uint16_t* hi,
 
 int dsin_f32_to_split(dsin_handle_t h, const float* x, uint16_t* hi, uint16_t* lo, int64_t count,
                       void* stream) {
-  DSIN_REQUIRE(h, x && hi && lo && count > 0, "bad argument");
+  DSIN_REQUIRE(h, x && hi && count > 0, "bad argument");
   f32_to_split_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       x, (__half*)hi, (__half*)lo, count);
   DSIN_LAUNCHED(h);
@@ -168,7 +168,7 @@ int dsin_f32_to_split(dsin_handle_t h, const float* x, uint16_t* hi, uint16_t* l
 
 int dsin_split_to_f32(dsin_handle_t h, const uint16_t* hi, const uint16_t* lo, float* y, int64_t count,
                       void* stream) {
-  DSIN_REQUIRE(h, y && hi && lo && count > 0, "bad argument");
+  DSIN_REQUIRE(h, y && hi && count > 0, "bad argument");
   split_to_f32_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const __half*)hi, (const __half*)lo, y, count);
   DSIN_LAUNCHED(h);

@@ -16,12 +16,10 @@
 // software pipeline across its CTAs.  All CTAs of a launch must be co-resident (cooperative launch).
 // The encoder does not need the schedule at all (every symbol is known): run_codec() takes the full-volume path
 // (probclass.cu pc1_symbol_tables + pc_symbol_coder_kernel); the wavefront kernel in encode mode gives the same
-// bytes and is kept as a cross-check (DSIN_PC_ENCODE_WAVEFRONT=1).
+// bytes and is kept as a cross-check (dsin_pc_encode_wavefront).
 //
 // Determinism.  Every activation is an fmaf chain in the order of oracle/pc_codec.c (bias; live taps in raster
 // order; input channels ascending); exp is a fixed polynomial; only correctly rounded IEEE operations are used.
-#include <stdlib.h>
-
 #include "pc_codec_common.cuh"
 
 namespace {
@@ -505,7 +503,7 @@ constexpr size_t kSmemBytes =
     (size_t)MAXPOS * MAXL * sizeof(uint32_t) + (size_t)MAXPOS * NT * K * sizeof(float) +
     (size_t)(3 * 2 * MAXH * K + MAXH) * sizeof(float) + (size_t)(MAXPOS + 1) * sizeof(int) + sizeof(long long) + WIN;
 
-int run_codec(dsin_handle_t h, int decode, int64_t* symbols, int n, int c, int hh, int ww, const float* centers, int L,
+int run_codec(dsin_handle_t h, int decode, bool wavefront_encode, int64_t* symbols, int n, int c, int hh, int ww, const float* centers, int L,
               const float* const* wb, int k, int nstreams, uint8_t* bytes, int64_t cap, int64_t* sizes, int* status_out,
               void* workspace, cudaStream_t st) {
   DSIN_REQUIRE(h, symbols && centers && wb && bytes && sizes && workspace && status_out, "null pointer");
@@ -515,7 +513,6 @@ int run_codec(dsin_handle_t h, int decode, int64_t* symbols, int n, int c, int h
   DSIN_REQUIRE(h, nstreams >= 1 && nstreams <= 64, "1..64 streams per image");
   DSIN_REQUIRE(h, (ww + 5) / 5 + 1 <= MAXPOS, "volume wider than 159 symbols (one CTA walks a slice 33 positions at a time)");
   DSIN_REQUIRE(h, hh + 6 <= MAXH, "volume taller than 58 symbols (rows of the shared-memory rings)");
-  static const bool wavefront_encode = getenv("DSIN_PC_ENCODE_WAVEFRONT") != nullptr;
   if (!decode && !wavefront_encode && L == 6 && (ww + 4) / 5 + 1 <= 32) {
     // every symbol is known: frequency tables for the whole volume in parallel (probclass.cu), then one CTA per
     // stream range-codes its symbols.  Same bytes as the wavefront kernel in encode mode.
@@ -534,11 +531,11 @@ int run_codec(dsin_handle_t h, int decode, int64_t* symbols, int n, int c, int h
     DSIN_LAUNCHED(h);
     return DSIN_OK;
   }
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[DSIN_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
+  if (!configured[h->device]) {
     if (cudaFuncSetAttribute(pc_codec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
       return dsin_fail(h, DSIN_ERR_CUDA, "%s: cannot raise dynamic shared memory", __func__);
-    configured = true;
+    configured[h->device] = true;
   }
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pc_codec_kernel, THREADS, kSmemBytes) != cudaSuccess || per_sm < 1)
@@ -585,14 +582,21 @@ int64_t dsin_pc_codec_workspace_bytes(int n, int c, int hh, int ww) {
 int dsin_pc_encode(dsin_handle_t h, const int64_t* symbols, int n, int c, int hh, int ww, const float* centers, int L,
                    const float* const* weights, int k, int nstreams, uint8_t* bytes, int64_t cap, int64_t* sizes,
                    int* status, void* workspace, void* stream) {
-  return run_codec(h, 0, const_cast<int64_t*>(symbols), n, c, hh, ww, centers, L, weights, k, nstreams, bytes, cap, sizes,
+  return run_codec(h, 0, false, const_cast<int64_t*>(symbols), n, c, hh, ww, centers, L, weights, k, nstreams, bytes, cap, sizes,
                    status, workspace, (cudaStream_t)stream);
+}
+
+int dsin_pc_encode_wavefront(dsin_handle_t h, const int64_t* symbols, int n, int c, int hh, int ww, const float* centers,
+                             int L, const float* const* weights, int k, int nstreams, uint8_t* bytes, int64_t cap,
+                             int64_t* sizes, int* status, void* workspace, void* stream) {
+  return run_codec(h, 0, true, const_cast<int64_t*>(symbols), n, c, hh, ww, centers, L, weights, k, nstreams, bytes, cap,
+                   sizes, status, workspace, (cudaStream_t)stream);
 }
 
 int dsin_pc_decode(dsin_handle_t h, const uint8_t* bytes, int64_t cap, const int64_t* sizes, int n, int c, int hh, int ww,
                    const float* centers, int L, const float* const* weights, int k, int nstreams, int64_t* symbols,
                    int* status, void* workspace, void* stream) {
-  return run_codec(h, 1, symbols, n, c, hh, ww, centers, L, weights, k, nstreams, const_cast<uint8_t*>(bytes), cap,
+  return run_codec(h, 1, false, symbols, n, c, hh, ww, centers, L, weights, k, nstreams, const_cast<uint8_t*>(bytes), cap,
                    const_cast<int64_t*>(sizes), status, workspace, (cudaStream_t)stream);
 }
 

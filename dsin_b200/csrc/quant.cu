@@ -7,7 +7,9 @@
 
 __global__ void heatmap_quantize_kernel(const float* __restrict__ z33, const float* __restrict__ centers,
                                         int L, int64_t npix, int hw, int c, float* __restrict__ qbar_nhwc,
-                                        float* __restrict__ qbar_nchw, int64_t* __restrict__ sym_nchw) {
+                                        float* __restrict__ qbar_nchw, int64_t* __restrict__ sym_nchw,
+                                        float* __restrict__ qhard_nchw, float* __restrict__ z_nchw,
+                                        float* __restrict__ heat_nchw) {
   __shared__ float s_c[DSIN_MAX_CENTERS];
   if (threadIdx.x < L) s_c[threadIdx.x] = centers[threadIdx.x];
   __syncthreads();
@@ -65,17 +67,21 @@ __global__ void heatmap_quantize_kernel(const float* __restrict__ z33, const flo
   int64_t o = (img * c + ch) * hw + p_in;
   if (qbar_nchw) qbar_nchw[o] = qbar;
   if (sym_nchw) sym_nchw[o] = (int64_t)sym;
+  if (qhard_nchw) qhard_nchw[o] = qhard;  // EncoderOutput.qhard / .z / .heatmap (src/autoencoder_imgcomp.py:239-245)
+  if (z_nchw) z_nchw[o] = z;
+  if (heat_nchw) heat_nchw[o] = h3;
 }
 
 extern "C" int dsin_heatmap_quantize(dsin_handle_t h, const float* z33, const float* centers, int L, int n,
                                      int hh, int ww, int c, float* qbar_nhwc, float* qbar_nchw,
-                                     int64_t* symbols_nchw, void* stream) {
+                                     int64_t* symbols_nchw, float* qhard_nchw, float* z_nchw,
+                                     float* heatmap_nchw, void* stream) {
   DSIN_REQUIRE(h, z33 && centers && n > 0 && hh > 0 && ww > 0 && c > 0, "bad argument");
   DSIN_REQUIRE(h, L >= 1 && L <= DSIN_MAX_CENTERS, "1 <= L <= 16");
   int64_t npix = (int64_t)n * hh * ww;
   int64_t tot = npix * c;
   heatmap_quantize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      z33, centers, L, npix, hh * ww, c, qbar_nhwc, qbar_nchw, symbols_nchw);
+      z33, centers, L, npix, hh * ww, c, qbar_nhwc, qbar_nchw, symbols_nchw, qhard_nchw, z_nchw, heatmap_nchw);
   DSIN_LAUNCHED(h);
   return DSIN_OK;
 }

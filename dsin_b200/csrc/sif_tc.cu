@@ -442,11 +442,11 @@ int sif_tc_match(dsin_handle_t h, const float* q, const float* r, const float* p
   p.use_mask = use_mask;
   p.kh = -4.0f / ((0.5f * hh) * (0.5f * hh));
   p.kw = -4.0f / ((0.5f * ww) * (0.5f * ww));
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[DSIN_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
+  if (!configured[h->device]) {
     if (cudaFuncSetAttribute(sif_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
       return dsin_fail(h, DSIN_ERR_CUDA, "%s: cannot raise dynamic shared memory", __func__);
-    configured = true;
+    configured[h->device] = true;
   }
   const int grid = p.total_units < h->sm_count ? p.total_units : h->sm_count;
   sif_tc_kernel<<<grid, 320, SMEM_BYTES, st>>>(tm_q, tm_s, p);

@@ -40,23 +40,23 @@ def _chk(t, dtype=torch.float32):
     return t
 
 
-def concat_normalize_split32(xdec_nhwc, ysyn_nhwc):
+def concat_normalize_split32(xdec_nhwc, ysyn_nhwc, with_lo=True):
     h = handle()
     n, hh, ww, _ = xdec_nhwc.shape
     hi = torch.empty((n, hh, ww, 32), dtype=torch.float16, device=xdec_nhwc.device)
-    lo = torch.empty((n, hh, ww, 32), dtype=torch.float16, device=xdec_nhwc.device)
+    lo = torch.empty((n, hh, ww, 32), dtype=torch.float16, device=xdec_nhwc.device) if with_lo else None
     h.check(h.lib.dsin_concat_normalize_split32(h.ptr, _p(_chk(xdec_nhwc)), _p(_chk(ysyn_nhwc)), _p(hi), _p(lo), n,
                                                 hh, ww, _stream()))
     return hi, lo
 
 
-def nchw_to_s2d_split32(x):
+def nchw_to_s2d_split32(x, with_lo=True):
     """(n,3,H,W) fp32 image -> normalised space-to-depth(2) split-fp16 (n,H/2,W/2,32) pair."""
     h = handle()
     n, c, hh, ww = x.shape
     assert c == 3 and hh % 2 == 0 and ww % 2 == 0
     hi = torch.empty((n, hh // 2, ww // 2, 32), dtype=torch.float16, device=x.device)
-    lo = torch.empty((n, hh // 2, ww // 2, 32), dtype=torch.float16, device=x.device)
+    lo = torch.empty((n, hh // 2, ww // 2, 32), dtype=torch.float16, device=x.device) if with_lo else None
     h.check(h.lib.dsin_nchw_to_s2d_split32(h.ptr, _p(_chk(x)), _p(hi), _p(lo), n, hh, ww, _stream()))
     return hi, lo
 
@@ -180,11 +180,11 @@ def conv2d(x, layer, res1=None, res2=None, scale=None, shift=None, act=None, pos
     return y
 
 
-def f32_to_split(x):
-    """fp32 tensor -> (hi, lo) fp16 planes with x ~= hi + lo (22-bit)."""
+def f32_to_split(x, with_lo=True):
+    """fp32 tensor -> (hi, lo) fp16 planes with x ~= hi + lo (22-bit); with_lo=False: (fp16(x), None)."""
     h = handle()
     hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
-    lo = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.float16, device=x.device) if with_lo else None
     h.check(h.lib.dsin_f32_to_split(h.ptr, _p(_chk(x)), _p(hi), _p(lo), x.numel(), _stream()))
     return hi, lo
 
@@ -192,8 +192,7 @@ def f32_to_split(x):
 def split_to_f32(hi, lo):
     h = handle()
     y = torch.empty(hi.shape, dtype=torch.float32, device=hi.device)
-    h.check(h.lib.dsin_split_to_f32(h.ptr, _p(_chk(hi, torch.float16)), _p(_chk(lo, torch.float16)), _p(y),
-                                    hi.numel(), _stream()))
+    h.check(h.lib.dsin_split_to_f32(h.ptr, _p(_chk(hi, torch.float16)), _p(lo), _p(y), hi.numel(), _stream()))
     return y
 
 
@@ -223,6 +222,9 @@ class ConvTC(object):
 Conv3x3TC = ConvTC
 
 CONV_PAIR_SHARED = 1
+CONV_NO_CTA_PAIR = 2             # cross-check: one-CTA kernel for a 128->128 layer
+CONV_NO_WEIGHT_STATIONARY = 4    # cross-check: tap-streaming CTA-pair kernel for a terms = 1 trunk layer
+CONV_WS_NO_BASE_OFFSET = 8       # diagnostic
 
 
 class _PairDesc(object):
@@ -251,8 +253,10 @@ class PairSharedTC(object):
 
 
 
-def conv_tc(x, tcl, res1=None, res2=None, terms=3, out_f32=False, post=None, prof=None):
-    """x: (hi, lo) split-fp16 NHWC pair.  Returns a split pair, or an fp32 NHWC tensor if out_f32."""
+def conv_tc(x, tcl, res1=None, res2=None, terms=3, out_f32=False, post=None, prof=None, flags=0):
+    """x: (hi, lo) split-fp16 NHWC pair.  Returns a split pair, or an fp32 NHWC tensor if out_f32.
+    terms == 1 (fp16 operands) reads the hi planes only and writes (hi, None): the fp16-operand passes keep
+    single-plane fp16 activations, which halves their HBM traffic."""
     h = handle()
     xh, xl = x
     L = tcl.layer
@@ -270,11 +274,13 @@ def conv_tc(x, tcl, res1=None, res2=None, terms=3, out_f32=False, post=None, pro
     else:
         yf = None
         yh = torch.empty((n, oh, ow, L.cout), dtype=torch.float16, device=dev)
-        yl = torch.empty((n, oh, ow, L.cout), dtype=torch.float16, device=dev)
+        yl = torch.empty((n, oh, ow, L.cout), dtype=torch.float16, device=dev) if terms == 3 else None
     r1h, r1l = res1 if res1 is not None else (None, None)
     r2h, r2l = res2 if res2 is not None else (None, None)
+    if terms == 3:
+        assert xl is not None, "3-term layers need the lo plane of their input"
     d = ConvDesc(n, hh, ww, c, L.cout, L.kh, L.kw, L.stride, L.dilation, int(L.transposed), tcl.act,
-                 L.post if post is None else post, int(L.dilation_x), int(getattr(L, "flags", 0)))
+                 L.post if post is None else post, int(L.dilation_x), int(getattr(L, "flags", 0)) | int(flags))
     e0 = PROF.begin()
     h.check(h.lib.dsin_conv2d_tc(h.ptr, C.byref(d), terms, _p(_chk(xh, torch.float16)), _p(xl), _p(tcl.w_hi),
                                  _p(tcl.w_lo), _p(tcl.scale), _p(tcl.shift), _p(r1h), _p(r1l), _p(r2h), _p(r2l),
@@ -294,7 +300,8 @@ def conv3x3_tc(xh, xl, tcl, res1=None, res2=None, terms=3):
     return conv_tc((xh, xl), tcl, res1=res1, res2=res2, terms=terms)
 
 
-def heatmap_quantize(z33_nhwc, centers):
+def heatmap_quantize(z33_nhwc, centers, full=False):
+    """-> (qbar_nhwc, qbar_nchw, symbols) and, with full=True, also (qhard, z, heatmap), all NCHW."""
     h = handle()
     n, hh, ww, c1 = z33_nhwc.shape
     c = c1 - 1
@@ -302,8 +309,12 @@ def heatmap_quantize(z33_nhwc, centers):
     qbar_nhwc = torch.empty((n, hh, ww, c), dtype=torch.float32, device=dev)
     qbar_nchw = torch.empty((n, c, hh, ww), dtype=torch.float32, device=dev)
     sym = torch.empty((n, c, hh, ww), dtype=torch.int64, device=dev)
+    extra = [torch.empty((n, c, hh, ww), dtype=torch.float32, device=dev) for _ in range(3)] if full else [None] * 3
     h.check(h.lib.dsin_heatmap_quantize(h.ptr, _p(_chk(z33_nhwc)), _p(_chk(centers)), centers.numel(), n, hh, ww, c,
-                                        _p(qbar_nhwc), _p(qbar_nchw), _p(sym), _stream()))
+                                        _p(qbar_nhwc), _p(qbar_nchw), _p(sym), _p(extra[0]), _p(extra[1]),
+                                        _p(extra[2]), _stream()))
+    if full:
+        return qbar_nhwc, qbar_nchw, sym, extra[0], extra[1], extra[2]
     return qbar_nhwc, qbar_nchw, sym
 
 
@@ -467,8 +478,9 @@ def pc_stream_capacity(c, hh, ww, nstreams):
     return 2 * slices * hh * ww + 16
 
 
-def pc_encode(symbols, centers, wlist, nstreams=8):
-    """symbols (n,c,h,w) int64 CUDA -> (bytes (n,nstreams,cap) uint8, sizes (n,nstreams) int64, status int32[1])."""
+def pc_encode(symbols, centers, wlist, nstreams=8, wavefront=False):
+    """symbols (n,c,h,w) int64 CUDA -> (bytes (n,nstreams,cap) uint8, sizes (n,nstreams) int64, status int32[1]).
+    wavefront=True runs the decoder's wavefront kernel in encode mode (same bytes; cross-check)."""
     h = handle()
     n, c, hh, ww = symbols.shape
     dev = symbols.device
@@ -478,7 +490,8 @@ def pc_encode(symbols, centers, wlist, nstreams=8):
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     ws = torch.empty(int(h.lib.dsin_pc_codec_workspace_bytes(n, c, hh, ww)), dtype=torch.uint8, device=dev)
     ptrs = _pc_codec_ptrs(wlist)
-    h.check(h.lib.dsin_pc_encode(h.ptr, _p(_chk(symbols, torch.int64)), n, c, hh, ww, _p(_chk(centers)), int(centers.numel()),
+    fn = h.lib.dsin_pc_encode_wavefront if wavefront else h.lib.dsin_pc_encode
+    h.check(fn(h.ptr, _p(_chk(symbols, torch.int64)), n, c, hh, ww, _p(_chk(centers)), int(centers.numel()),
                                  ptrs, int(wlist[1].numel()), nstreams, _p(out), cap, _p(sizes), _p(status), _p(ws),
                                  _stream()))
     return out, sizes, status

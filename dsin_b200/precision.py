@@ -1,0 +1,48 @@
+"""Arithmetic policy of the tensor-core layers: how many tcgen05 MMAs each product is built from.
+
+Every activation / weight is held as a split-fp16 pair v = hi + lo (22-bit significand).
+  terms = 3   hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM   (fp32-class; decides integer outputs)
+  terms = 1   hi*hi only                                          (fp16 operands, fp32 accumulation)
+
+Which passes of AE.siNet_get_reconstructed (/root/reference/src/AE.py:132-148) need which:
+  * encoder(x) produces the symbols and hence bpp -- the integer / 1e-5 outputs.  Always 3-term.
+  * encoder(y) produces the symbols of the side image; a flipped symbol there changes y_dec discretely, so
+    it stays 3-term in the shipped policy.
+  * decoder(y), decoder(x) and the SI-Net produce float images only (gate: |d MS-SSIM| <= 1e-4).
+  * the probability model produces bits (gate: |d bpp| <= 1e-5): 3-term.
+
+The shipped policy is the fastest one that passes tests/test_gpu_parity.py::test_precision_policy_*; the
+measurements behind the choice are in DESIGN.md section 5 and profiles/r2_*precision*.json.
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+
+Policy = namedtuple("Policy", ["name", "enc_x", "enc_y", "dec", "sinet", "probclass"])
+
+EXACT = Policy("exact", 3, 3, 3, 3, 3)             # round-1 behaviour: every tensor-core layer fp32-class
+MIXED = Policy("mixed", 3, 3, 1, 1, 3)             # float-only passes on fp16 operands
+MIXED_Y1 = Policy("mixed_y1", 3, 1, 1, 1, 3)       # additionally encoder(y) on fp16 operands
+FAST = Policy("fast", 1, 1, 1, 1, 1)               # everything fp16 (symbols no longer reference-exact)
+
+DEC1 = Policy("dec1", 3, 3, 1, 3, 3)               # only the decoders on fp16 operands
+SINET1 = Policy("sinet1", 3, 3, 3, 1, 3)           # only the SI-Net on fp16 operands
+
+BY_NAME = {p.name: p for p in (EXACT, MIXED, MIXED_Y1, FAST, DEC1, SINET1)}
+
+DEFAULT = EXACT
+
+
+def get(policy):
+    if policy is None:
+        return DEFAULT
+    if isinstance(policy, Policy):
+        return policy
+    return BY_NAME[policy]
+
+
+def dtype_string(policy):
+    p = get(policy)
+    t = {3: "f16x2-split x3 MMA (fp32-class)", 1: "f16 x1 MMA"}
+    return ("tcgen05 fp32-accumulate: enc(x) %s, enc(y) %s, decoders %s, SI-Net %s, probclass %s; CUDA-core f32/f64 "
+            "elsewhere" % (t[p.enc_x], t[p.enc_y], t[p.dec], t[p.sinet], t[p.probclass]))

@@ -7,16 +7,14 @@ caller in the reference; ``encode_symbols`` / ``decode_symbols`` below are the c
 """
 from __future__ import annotations
 
-import os
-
 import numpy as np
 import torch
 
 from . import bitstream, ops, synth
 
 
-# "tc3"/"tc1": the two 24->24 layers on tcgen05 (split fp16 / fp16); "simt": all CUDA cores
-MODE = os.environ.get("DSIN_PROBCLASS_MODE", "tc3")
+# The two 24->24 layers and the head run on tcgen05; the all-CUDA-core kernel (ops.probclass_bits) is the
+# cross-check the tests call directly.
 
 
 def get_network_cls(pc_config):
@@ -83,7 +81,7 @@ class _ResShallow(object):
             self._codec.append(torch.from_numpy(packed).to(self.device))
             self._codec.append(torch.from_numpy(np.ascontiguousarray(W[P + name + "/biases"], np.float32)).to(self.device))
 
-    def bitcost(self, q, target_symbols, is_training=False, pad_value=0):
+    def bitcost(self, q, target_symbols, is_training=False, pad_value=0, terms=3):
         """q: qbar NCHW fp32, target_symbols NCHW int64 -> bits per symbol NCHW.  The fp64
         per-image sums ride along as ``._dsin_sum`` for bits_imgcomp.bitcost_to_bpp."""
         if is_training is True:
@@ -91,14 +89,12 @@ class _ResShallow(object):
         if q.dim() != 4:
             raise ValueError("expected NCHW, got {}".format(tuple(q.shape)))
         n, c, hh, ww = q.shape
-        if MODE in ("tc3", "tc1") and hh + 2 >= 8 and ww + 2 >= 16 and self.config.arch_param__k == 24:
-            if self._tc is None:
-                self._tc = ops.ProbclassTC(self.weights)
-            bits, sums = ops.probclass_bits_tc(q.contiguous(), target_symbols.contiguous(), self._tc,
-                                               float(pad_value), terms=3 if MODE == "tc3" else 1)
-        else:
-            bits, sums = ops.probclass_bits(q.contiguous(), target_symbols.contiguous(), self.weights,
-                                            float(pad_value), k=self.config.arch_param__k, L=self.L)
+        if hh + 2 < 8 or ww + 2 < 16 or self.config.arch_param__k != 24:
+            raise ValueError("dsin_b200 probclass: needs arch_param__k == 24 and a bottleneck of at least 6x14")
+        if self._tc is None:
+            self._tc = ops.ProbclassTC(self.weights)
+        bits, sums = ops.probclass_bits_tc(q.contiguous(), target_symbols.contiguous(), self._tc,
+                                           float(pad_value), terms=terms)
         bits._dsin_sum = sums
         return bits
 

@@ -7,17 +7,16 @@ y_syn_nhwc)`` additionally fuses the normalise+concat in front (src/AE.py:67-68)
 de-normalisation behind (src/AE.py:69)."""
 from __future__ import annotations
 
-import os
-
 import numpy as np
+import torch
 
 from . import ops, synth
 
-
-# "tc3": tcgen05 split-fp16 (fp32-class); "tc1": tcgen05 fp16; "simt": CUDA-core fp32
-MODE = os.environ.get("DSIN_SINET_MODE", "tc3")
-PAIR = os.environ.get("DSIN_SINET_PAIR", "1") != "0"  # pixel-pair form (128-byte TMA rows)
-PAIR_SHARED = os.environ.get("DSIN_SINET_PAIR_SHARED", "1") != "0"  # even dilation: no MMAs on zero blocks
+# Layer forms (all tcgen05, csrc/conv_tc.cu).  PAIR: the pixel-pair view (128-byte TMA rows) for the nine 3x3
+# layers; PAIR_SHARED: even dilations reuse the plain 32x32 slab for both pixels of a pair.  Module attributes so
+# that tests can compare the forms against each other; the product never changes them.
+PAIR = True
+PAIR_SHARED = True
 
 
 class SiNet(object):
@@ -81,54 +80,46 @@ class SiNet(object):
         layer.dilation_x = step
         return layer
 
-    def _run(self, net, post):
-        n, hh, ww, _ = net.shape
-        if MODE in ("tc3", "tc1") and hh >= 8 and ww >= 16:
-            terms = 3 if MODE == "tc3" else 1
-            if self._tc is None:
-                self._tc = [ops.ConvTC(layer) for layer in self.layers[1:]]
-            cur = ops.f32_to_split(ops.conv2d(net, self.layers[0]))  # g_conv1 has cin = 6: CUDA cores
-            for tcl in self._tc[:-1]:
+    def _layers_tc(self, cur, n, hh, ww, terms, post):
+        """cur: 32-channel split-fp16 NHWC pair (6 live channels) -> fp32 NHWC (n,hh,ww,3)."""
+        if hh < 8 or ww < 16:
+            raise ValueError("dsin_b200 SI-Net: image smaller than one 8x16 tensor-core tile")
+        if self._tc is None:
+            self._tc = [ops.ConvTC(layer) for layer in self.layers[1:]]
+        if self._tc_first is None:
+            self._tc_first = ops.ConvTC(self._first_padded)
+        use_pair = PAIR and ww % 2 == 0 and ww // 2 >= 16
+        for li, tcl in enumerate([self._tc_first] + self._tc[:-1]):
+            if use_pair and li in self._pair:
+                key = (li, PAIR_SHARED)
+                if key not in self._pair_tc:
+                    rate = self.RATES[li]
+                    if PAIR_SHARED and li >= 1 and rate % 2 == 0:  # parity-preserving: shared 32x32 slab
+                        self._pair_tc[key] = ops.PairSharedTC(self._tc[li - 1], rate)
+                    else:
+                        self._pair_tc[key] = ops.ConvTC(self._pair[li])
+                v = tuple(None if t is None else t.view(n, hh, ww // 2, 64) for t in cur)
+                o = ops.conv_tc(v, self._pair_tc[key], terms=terms,
+                                prof=("tc%d_conv3x3_32to32_pair", 2.0 * n * hh * ww * 9 * (6 if li == 0 else 32) * 32))
+                cur = tuple(None if t is None else t.view(n, hh, ww, 32) for t in o)
+            else:
                 cur = ops.conv_tc(cur, tcl, terms=terms)
-            return ops.conv_tc(cur, self._tc[-1], terms=terms, out_f32=True, post=post)
-        for layer in self.layers[:-1]:
-            net = ops.conv2d(net, layer)
-        return ops.conv2d(net, self.layers[-1], post=post)
+        return ops.conv_tc(cur, self._tc[-1], terms=terms, out_f32=True, post=post)
 
-    def __call__(self, input):  # noqa: A002 - reference argument name
+    def __call__(self, input, terms=3):  # noqa: A002 - reference argument name
+        """siNet(input[N,6,H,W]) -> [N,3,H,W] (src/siNet.py:29-41); the input is already normalised."""
+        n, c, hh, ww = input.shape
+        if c != 6:
+            raise ValueError("siNet expects 6 input channels, got %d" % c)
         net = ops.nchw_to_nhwc(input.contiguous())
-        return ops.nhwc_to_nchw(self._run(net, ops.POST_NONE))
+        pad = torch.zeros((n, hh, ww, 32), dtype=torch.float32, device=input.device)  # layout only: 6 -> 32 channels
+        pad[..., :6] = net
+        return ops.nhwc_to_nchw(self._layers_tc(ops.f32_to_split(pad, with_lo=terms == 3), n, hh, ww, terms, ops.POST_NONE))
 
-    def fused(self, x_dec_nhwc, y_syn_nhwc):
+    def fused(self, x_dec_nhwc, y_syn_nhwc, terms=3):
         n, hh, ww, _ = x_dec_nhwc.shape
-        if MODE in ("tc3", "tc1") and hh >= 8 and ww >= 16:
-            terms = 3 if MODE == "tc3" else 1
-            if self._tc is None:
-                self._tc = [ops.ConvTC(layer) for layer in self.layers[1:]]
-            if self._tc_first is None:
-                self._tc_first = ops.ConvTC(self._first_padded)
-            cur = ops.concat_normalize_split32(x_dec_nhwc, y_syn_nhwc)
-            use_pair = PAIR and ww % 2 == 0 and ww // 2 >= 16
-            for li, tcl in enumerate([self._tc_first] + self._tc[:-1]):
-                if use_pair and li in self._pair:
-                    if li not in self._pair_tc:
-                        rate = self.RATES[li]
-                        if PAIR_SHARED and li >= 1 and rate % 2 == 0:  # parity-preserving: shared 32x32 slab
-                            self._pair_tc[li] = ops.PairSharedTC(self._tc[li - 1], rate)
-                        else:
-                            self._pair_tc[li] = ops.ConvTC(self._pair[li])
-                    v = (cur[0].view(n, hh, ww // 2, 64), cur[1].view(n, hh, ww // 2, 64))
-                    o = ops.conv_tc(v, self._pair_tc[li], terms=terms,
-                                    prof=("tc%d_conv3x3_32to32_pair", 2.0 * n * hh * ww * 9 * (6 if li == 0 else 32) * 32))
-                    cur = (o[0].view(n, hh, ww, 32), o[1].view(n, hh, ww, 32))
-                else:
-                    cur = ops.conv_tc(cur, tcl, terms=terms)
-            out_nhwc = ops.conv_tc(cur, self._tc[-1], terms=terms, out_f32=True, post=ops.POST_DENORM)
-            out = ops.nhwc_to_nchw(out_nhwc)
-            out._dsin_nhwc = out_nhwc
-            return out
-        net = ops.concat_normalize(x_dec_nhwc, y_syn_nhwc)
-        out_nhwc = self._run(net, ops.POST_DENORM)
+        cur = ops.concat_normalize_split32(x_dec_nhwc, y_syn_nhwc, with_lo=terms == 3)
+        out_nhwc = self._layers_tc(cur, n, hh, ww, terms, ops.POST_DENORM)
         out = ops.nhwc_to_nchw(out_nhwc)
         out._dsin_nhwc = out_nhwc
         return out

@@ -80,7 +80,11 @@ typedef struct {
   int flags;      /* DSIN_CONV_PAIR_SHARED (tensor-core path, cin = cout = 64 = two pixels x 32 channels, even
                      dilation): the weights are the plain [taps][32][32] slab, applied to each pixel of the pair */
 } dsin_conv_desc_t;
-enum { DSIN_CONV_PAIR_SHARED = 1 };
+enum { DSIN_CONV_PAIR_SHARED = 1,
+       DSIN_CONV_NO_CTA_PAIR = 2, /* run a 128->128 layer on the one-CTA kernel (cross-check of the CTA-pair kernels) */
+       DSIN_CONV_NO_WEIGHT_STATIONARY = 4, /* terms = 1, 3x3 128->128: use the tap-streaming CTA-pair kernel instead of
+                                              the weight-stationary halo-tile kernel (cross-check) */
+       DSIN_CONV_WS_NO_BASE_OFFSET = 8 /* diagnostic: leave the shared-memory descriptor's base-offset field 0 */ };
 int dsin_conv2d(dsin_handle_t h, const dsin_conv_desc_t* d, const float* x, const float* w,
                 const float* scale, const float* shift, const float* res1, const float* res2,
                 float* y, void* stream);
@@ -126,10 +130,14 @@ int dsin_split_to_f32(dsin_handle_t h, const uint16_t* hi, const uint16_t* lo, f
  * quantizer._quantize1d (src/quantizer_imgcomp.py:43-95) + qbar (:132-133).
  * z33: NHWC (n,hh,ww,c+1) output of to_bn; centers: (L) fp32, L <= 16.
  * Outputs: qbar_nhwc (n,hh,ww,c) for the decoder; qbar_nchw (n,c,hh,ww) for the probability
- * model; symbols_nchw int64 (n,c,hh,ww).  Any output pointer may be NULL. */
+ * model; symbols_nchw int64 (n,c,hh,ww); and the remaining fields of the reference's EncoderOutput
+ * (src/autoencoder_imgcomp.py:15,239-245), all (n,c,hh,ww) fp32: qhard_nchw = centers[symbols],
+ * z_nchw = the heatmap-masked bottleneck the quantiser saw, heatmap_nchw = the 3-D heatmap.
+ * Any output pointer may be NULL. */
 int dsin_heatmap_quantize(dsin_handle_t h, const float* z33_nhwc, const float* centers, int L,
                           int n, int hh, int ww, int c, float* qbar_nhwc, float* qbar_nchw,
-                          int64_t* symbols_nchw, void* stream);
+                          int64_t* symbols_nchw, float* qhard_nchw, float* z_nchw,
+                          float* heatmap_nchw, void* stream);
 
 /* ---- K4: 3-D masked-conv probability model -> bits ---------------------------------------
  * Replaces _Network3D.bitcost / _ResShallow._logits / conv3d / pad_for_probclass3d
@@ -212,6 +220,10 @@ int64_t dsin_pc_codec_workspace_bytes(int n, int c, int hh, int ww);
 int dsin_pc_encode(dsin_handle_t h, const int64_t* symbols, int n, int c, int hh, int ww, const float* centers, int L,
                    const float* const* weights, int k, int nstreams, uint8_t* bytes, int64_t cap, int64_t* sizes,
                    int* status, void* workspace, void* stream);
+/* Same bytes as dsin_pc_encode, produced by the decoder's wavefront kernel run in encode mode (cross-check). */
+int dsin_pc_encode_wavefront(dsin_handle_t h, const int64_t* symbols, int n, int c, int hh, int ww, const float* centers,
+                             int L, const float* const* weights, int k, int nstreams, uint8_t* bytes, int64_t cap,
+                             int64_t* sizes, int* status, void* workspace, void* stream);
 int dsin_pc_decode(dsin_handle_t h, const uint8_t* bytes, int64_t cap, const int64_t* sizes, int n, int c, int hh, int ww,
                    const float* centers, int L, const float* const* weights, int k, int nstreams, int64_t* symbols,
                    int* status, void* workspace, void* stream);

@@ -30,7 +30,7 @@ def configs(H, W):
     return ae_config, pc_config
 
 
-def make_ae(H, W, weights):
+def make_ae(H, W, weights, precision=None):
     from dsin_b200.AE import AE
     from dsin_b200.decoder_imgcomp import decoder
     from dsin_b200.encoder_imgcomp import encoder
@@ -38,7 +38,8 @@ def make_ae(H, W, weights):
     from dsin_b200.siFull_img import SI_full_img
     from dsin_b200.siNet import siNet
     ae_config, pc_config = configs(H, W)
-    return AE(ae_config, pc_config, encoder, decoder, siFinder, SI_full_img, siNet, CFG, weights=weights)
+    return AE(ae_config, pc_config, encoder, decoder, siFinder, SI_full_img, siNet, CFG, weights=weights,
+              precision=precision)
 
 
 def symbol_report(sym_gpu, x_np, W, margin_tol=1e-3):

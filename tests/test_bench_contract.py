@@ -8,9 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_json_contract():
-    env = dict(os.environ, DSIN_BENCH_HW="80x144")
+    env = dict(os.environ)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0"], capture_output=True, text=True, env=env, timeout=300, cwd=ROOT)
+                          "--warmup", "0", "--hw", "80x144"], capture_output=True, text=True, env=env, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -23,10 +23,11 @@ def test_reference_arm_json_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"]
+    assert "80x144" in d["metric"] and "NOT the BASELINE geometry" in d["metric"]  # a shrunk run says so itself
 
 
 def test_non_zero_ranks_of_reference_arm_exit_quietly():
-    env = dict(os.environ, DSIN_BENCH_HW="80x144", RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120, cwd=ROOT)
+                          "--warmup", "0", "--hw", "80x144"], capture_output=True, text=True, env=env, timeout=120, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == ""

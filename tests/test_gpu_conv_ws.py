@@ -1,0 +1,76 @@
+"""The weight-stationary, halo-tile trunk kernel (csrc/conv_ws.cu; fp16 operands, one MMA per product) against
+a float64 convolution of the very fp16 values it consumed, and against the tap-streaming CTA-pair kernel it
+replaces for the fp16-operand passes (src/autoencoder_imgcomp.py:229-234,257-262,275-288)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dsin_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _case(n, hh, ww, nres, act, seed=0):
+    from dsin_b200 import ops
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, 128, hh, ww)).astype(np.float32)
+    w = (rng.standard_normal((3, 3, 128, 128)) / np.sqrt(9 * 128)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, 128).astype(np.float32)
+    shift = rng.standard_normal(128).astype(np.float32)
+    layer = ops.ConvLayer(w, scale, shift, act=act)
+    tcl = ops.ConvTC(layer)
+    xh = _nhwc(torch.tensor(x).cuda()).half()
+    res = [_nhwc(torch.tensor(rng.standard_normal((n, 128, hh, ww)).astype(np.float32)).cuda()).half()
+           for _ in range(nres)]
+    return ops, tcl, w, scale, shift, xh, res
+
+
+def _ref64(tcl, w, scale, shift, xh, res, act):
+    """float64 result from the fp16 operands the kernel reads: x as fp16, weights as their packed fp16 hi plane."""
+    wscale = (torch.tensor(scale).cuda() / tcl.scale).cpu().double()          # the per-cout power of two
+    w_hi = tcl.w_hi.cpu().double().reshape(3, 3, 128, 128).permute(0, 1, 3, 2)  # [ky][kx][cin][cout], scaled
+    xq = xh.permute(0, 3, 1, 2).cpu().double()
+    y = O.conv2d_same(xq, w_hi.numpy()) / wscale.view(1, -1, 1, 1)
+    y = y * torch.tensor(scale).double().view(1, -1, 1, 1) + torch.tensor(shift).double().view(1, -1, 1, 1)
+    if act:
+        y = torch.relu(y)
+    for r in res:
+        y = y + r.permute(0, 3, 1, 2).cpu().double()
+    return y
+
+
+@pytest.mark.parametrize("shape", [(2, 20, 36), (1, 80, 306), (3, 9, 17), (1, 16, 8), (2, 33, 70)])
+@pytest.mark.parametrize("nres", [0, 1, 2])
+def test_conv_ws_matches_float64_and_streaming_kernel(shape, nres):
+    n, hh, ww = shape
+    act = 1 if nres < 2 else 0
+    ops, tcl, w, scale, shift, xh, res = _case(n, hh, ww, nres, act, seed=hh + nres)
+    r1 = (res[0], None) if nres > 0 else None
+    r2 = (res[1], None) if nres > 1 else None
+    y_ws, lo = ops.conv_tc((xh, None), tcl, res1=r1, res2=r2, terms=1)
+    assert lo is None and y_ws.dtype == torch.float16
+    y_st, _ = ops.conv_tc((xh, None), tcl, res1=r1, res2=r2, terms=1, flags=ops.CONV_NO_WEIGHT_STATIONARY)
+    ref = _ref64(tcl, w, scale, shift, xh, res, act)
+    got = y_ws.permute(0, 3, 1, 2).cpu().double()
+    old = y_st.permute(0, 3, 1, 2).cpu().double()
+    # fp32 accumulation of exact products, then ONE rounding to fp16 (relative 2^-11): the two kernels differ only in
+    # summation order (fp32), so they agree to one fp16 ulp; against float64 the bound is half an ulp + fp32 noise
+    tol = 2.0 ** -10 * torch.clamp(ref.abs(), min=1.0)
+    assert bool(((got - ref).abs() <= tol).all()), float(((got - ref).abs() / tol).max())
+    assert bool(((got - old).abs() <= 2 * tol).all())
+    frac_equal = float((got == old).double().mean())
+    assert frac_equal > 0.99, frac_equal
+
+
+def test_conv_ws_is_the_default_for_fp16_operand_trunk_layers():
+    """The dispatch: terms = 1, 3x3, 128 -> 128 runs conv_ws_kernel (one more launch on the handle, same result whether
+    the residual is given or not) and a lo residual plane falls back to the streaming kernel."""
+    ops, tcl, w, scale, shift, xh, res = _case(1, 32, 48, 1, 1, seed=5)
+    y0, _ = ops.conv_tc((xh, None), tcl, res1=(res[0], None), terms=1)
+    lo = torch.zeros_like(res[0])
+    y1, _ = ops.conv_tc((xh, None), tcl, res1=(res[0], lo), terms=1)  # lo plane present -> streaming kernel
+    assert float((y0.float() - y1.float()).abs().max()) <= 2.0 ** -9 * float(y0.float().abs().max())

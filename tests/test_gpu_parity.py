@@ -392,23 +392,24 @@ def test_msssim_kernel_batch_matches_oracle_full_size():
 
 @pytest.mark.parametrize("mode", ["simt", "tc3"])
 def test_probclass_modes_match_oracle(mode):
-    from dsin_b200 import probclass_imgcomp as pcm
+    """The tcgen05 probability model (the product path) and the all-CUDA-core kernel (cross-check, reached through
+    the C ABI only from here) against the oracle."""
+    from dsin_b200 import ops
     W = calibrated_weights(0)
-    old = pcm.MODE
-    pcm.MODE = mode
-    try:
-        ae = make_ae(80, 144, W)
-        rng = np.random.default_rng(6)
-        c = W[O.ENC + "centers"]
-        sym = torch.tensor(rng.integers(0, 6, (2, 32, 40, 153)))
-        q = torch.tensor(c)[sym]
-        ref = O.probclass_bitcost(q, sym, W)
+    ae = make_ae(80, 144, W)
+    rng = np.random.default_rng(6)
+    c = W[O.ENC + "centers"]
+    sym = torch.tensor(rng.integers(0, 6, (2, 32, 40, 153)))
+    q = torch.tensor(c)[sym]
+    ref = O.probclass_bitcost(q, sym, W)
+    if mode == "tc3":
         bits = ae.pc_imgcomp.bitcost(q.cuda(), sym.cuda(), is_training=False, pad_value=float(c[0]))
-        assert float((bits.cpu() - ref).abs().max()) < 1e-4
         sums = bits._dsin_sum.cpu()
-        assert torch.allclose(sums, ref.double().reshape(2, -1).sum(1), rtol=2e-7)
-    finally:
-        pcm.MODE = old
+    else:
+        bits, sums = ops.probclass_bits(q.cuda().contiguous(), sym.cuda().contiguous(), ae.pc_imgcomp.weights, float(c[0]))
+        sums = sums.cpu()
+    assert float((bits.cpu() - ref).abs().max()) < 1e-4
+    assert torch.allclose(sums, ref.double().reshape(2, -1).sum(1), rtol=2e-7)
 
 
 # ----------------------------------------------------------------------------- other BASELINE configs
@@ -475,7 +476,7 @@ def test_cabi_error_codes_and_messages():
     rc = lib.dsin_conv2d(h.ptr, C.byref(d), C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()), None, None, None,
                          None, C.c_void_p(x.data_ptr()), None)
     assert rc == -1 and b"stride" in lib.dsin_last_error(h.ptr)
-    rc = lib.dsin_heatmap_quantize(h.ptr, None, None, 6, 1, 1, 1, 1, None, None, None, None)
+    rc = lib.dsin_heatmap_quantize(h.ptr, None, None, 6, 1, 1, 1, 1, None, None, None, None, None, None, None)
     assert rc == -1
     rc = lib.dsin_sif_prepare(h.ptr, C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()), 1, 30, 50, 20, 24,
                               C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()),
