@@ -205,15 +205,15 @@ class AE(object):
         P = self.precision
         if P.enc_x == P.enc_y:
             z = self._encode(torch.cat([y, x], dim=0), self.ae_imgcomp, is_training=False, terms=P.enc_x)
-            qall, qx, sx = z.qbar, z.qbar[B:], z.symbols[B:]
+            qall, qx, sx, sy = z.qbar, z.qbar[B:], z.symbols[B:], z.symbols[:B]
         else:  # the two encoder passes run at different operand precision: two launches per layer
             zy = self._encode(y, self.ae_imgcomp, is_training=False, terms=P.enc_y)
             zx = self._encode(x, self.ae_imgcomp, is_training=False, terms=P.enc_x)
-            qall, qx, sx = self._cat_qbar(zy.qbar, zx.qbar), zx.qbar, zx.symbols
+            qall, qx, sx, sy = self._cat_qbar(zy.qbar, zx.qbar), zx.qbar, zx.symbols, zy.symbols
         dec = self._decode(qall, self.ae_imgcomp, is_training=False, terms=P.dec)
         bc = self.pc_imgcomp.bitcost(qx, sx, is_training=False,
                                      pad_value=self.pc_imgcomp.auto_pad_value(self.ae_imgcomp), terms=P.probclass)
-        return {"dec": dec, "symbols": sx, "qbar": qx, "bits": bc, "bits_sum": bc._dsin_sum}
+        return {"dec": dec, "symbols": sx, "symbols_y": sy, "qbar": qx, "bits": bc, "bits_sum": bc._dsin_sum}
 
     @staticmethod
     def _cat_qbar(qa, qb):

@@ -558,7 +558,6 @@ extern "C" int dsin_conv2d_tc(dsin_handle_t h, const dsin_conv_desc_t* d, int te
       a.scale = scale; a.shift = shift;
       a.r1 = p.r1h; a.r2 = p.r2h; a.y = p.yh;
       a.n = d->n; a.OH = p.OH; a.OW = p.OW; a.act = d->act;
-      a.base_offset_mode = (d->flags & DSIN_CONV_WS_NO_BASE_OFFSET) ? 0 : 1;
       return conv_ws_launch(h, (const __half*)x_hi, (const __half*)w_hi, a, st);
     }
     if (use_pairs && KC == 64 && NPAD == 128 && d->cout == 128 && y_hi && !y_f32 && d->post == DSIN_POST_NONE &&

@@ -46,6 +46,5 @@ struct ConvWsArgs {
   __half* y;
   int n, OH, OW, act;
   int tiles_w, tiles_h, total_tiles;  // filled by conv_ws_launch
-  int base_offset_mode;               // 1: the tap's column shift is declared in the descriptor's base-offset field
 };
 int conv_ws_launch(dsin_handle_t h, const __half* x, const __half* w_packed, const ConvWsArgs& a, cudaStream_t st);

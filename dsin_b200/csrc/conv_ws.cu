@@ -10,14 +10,22 @@
 //     9 taps x 64 couts x 128 cin fp16 = 144 KB, loaded once (CTA pair, cta_group::2: each CTA supplies 64 of the
 //     128 couts of the N = 128 operand);
 //   * the activation tile is loaded ONCE with its halo -- 16 x 8 output pixels read 18 x 10 input pixels -- and
-//     the nine taps are nine shared-memory descriptors into that one tile: the tile is stored at a 16-pixel row
-//     pitch (2048 B, so every 8-pixel row group starts at a fixed phase of the 128-byte swizzle), the tap's row
-//     shift is a multiple of the pitch, and its column shift (dx+1) x 128 B goes into the descriptor start
-//     address together with the descriptor's 3-bit base-offset field (the swizzle phase of the first row).
-//     L2 -> shared traffic per tile: 2 x 36 KB instead of 432 KB.
-//   * residual inputs are NOT fed through the tensor pipe (conv_tc2's identity MMAs would cost 11-22 % here):
-//     every epilogue thread prefetches its pixel's residual channels into registers while the tile's MMAs are
-//     still running, so the loads are off the critical path.
+//     the nine taps are nine shared-memory descriptors into that one tile: output row r of the tile is one 8-row
+//     group of the MMA's M dimension (8 pixels x 128 B), groups one stored row (10 pixels, 1280 B) apart (SBO), and
+//     a tap only moves
+//     the descriptor's start address by (ky x pitch + kx) x 128 B.  This works because both TMA and the UMMA
+//     descriptor derive the 128-byte-swizzle phase from the ABSOLUTE shared-memory address bits [7:9] (measured:
+//     tools/conv_ws_debug.py -- with start addresses that are only 128-byte aligned the operand rows come out
+//     right with the descriptor's base-offset field left 0, and wrong with it set).
+//     L2 -> shared traffic per tile: 2 x 22.5 KB instead of 432 KB; the next tile's boxes are prefetched into L2 one tile ahead.
+//   * the epilogue is COALESCED.  A TMEM row is a pixel, so a warp's natural 16-byte accesses land in 32
+//     different 128-byte lines (pixels are 256 B apart): 32 L1TEX wavefronts per instruction, ~2000 cycles of
+//     stores and ~2000 per residual tensor per tile against 4608 MMA cycles -- the first version of this kernel
+//     was bound by exactly that (profiles/r2_v2_ncu_conv_ws.txt: tensor pipe 59 % / 40 % with residuals).  Now
+//     every epilogue warp owns a 4 KB swizzled staging block (its 32 pixels x 64 channels): results go
+//     registers -> staging -> ONE TMA store per warp and tile (which also clips partial tiles), and residual
+//     tensors come in through cp.async with 4 pixels x 128 contiguous bytes per instruction, are read back
+//     conflict-free, and are fetched while the tile's MMAs are still running.
 // TMA out-of-bounds zero fill provides the SAME padding as before (negative / past-the-end box origins).
 #include "tc_common.cuh"
 #include "conv_tc.cuh"
@@ -28,19 +36,44 @@ namespace {
 
 constexpr int TR = 16, TC = 8;              // output tile: 16 rows x 8 pixels = 128 GEMM rows, m = r * 8 + c
 constexpr int HALO_R = TR + 2;              // 18 input rows
-constexpr int PITCH = 16;                   // pixels per stored row (10 are used)
-constexpr int A_STAGE = HALO_R * PITCH * 128;  // 36 864 B: one 64-channel chunk of the halo tile
+constexpr int PITCH = TC + 2;               // 10 input pixels per stored row, stored densely (1280-byte rows)
+constexpr int A_BYTES = HALO_R * PITCH * 128;  // 23 040 B: one 64-channel chunk of the halo tile
+constexpr int A_STAGE = (A_BYTES + 1023) / 1024 * 1024;  // stage bases stay 1024-byte aligned
 constexpr int W_SLAB = 64 * 128;            // one (tap, chunk) slab of this CTA's 64 couts
 constexpr int W_BYTES = 18 * W_SLAB;        // 147 456 B
 constexpr int NSTAGE = 2;
-constexpr int SMEM_BYTES = W_BYTES + NSTAGE * A_STAGE + 2048 + 1024;
+constexpr int STG_WARP = 32 * 128;          // one epilogue warp's staging block: 32 pixels x 64 channels fp16
+constexpr int STG_BYTES = 8 * STG_WARP;
+constexpr int SMEM_BYTES = W_BYTES + NSTAGE * A_STAGE + STG_BYTES + 2048 + 1024;
 
-__device__ __forceinline__ uint4 ld_nc16(const void* p) {
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;  // src-size 0: zero fill, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ uint4 lds16(uint32_t saddr) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
   return r;
+}
+__device__ __forceinline__ void sts16(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 
 __device__ __forceinline__ void add_half8(float* f, const uint4& u) {
@@ -55,13 +88,14 @@ __device__ __forceinline__ void add_half8(float* f, const uint4& u) {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 conv_ws_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-               const __grid_constant__ ConvWsArgs p) {
+               const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ ConvWsArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* wsm = smem;                       // [tap 9][chunk 2][64 couts][128 B], 128-byte swizzle
   uint8_t* tiles = smem + W_BYTES;           // NSTAGE halo chunks
-  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + NSTAGE * A_STAGE);
+  uint8_t* stg = tiles + NSTAGE * A_STAGE;   // 8 x 4 KB epilogue staging blocks (1024-byte aligned)
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg + STG_BYTES);
   uint64_t* empty = full + NSTAGE;
   uint64_t* tfull = empty + NSTAGE;
   uint64_t* tempty = tfull + 2;
@@ -86,6 +120,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     fence_barrier_init();
     prefetch_tmap(&tm_x);
     prefetch_tmap(&tm_w);
+    prefetch_tmap(&tm_y);
   }
   for (int i = threadIdx.x; i < 128; i += blockDim.x) {
     s_scale[i] = p.scale[i];
@@ -115,11 +150,17 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       if (tile >= p.total_tiles) tile = p.total_tiles - 1;  // odd tail: recompute a valid tile, never stored
       const int tw = tile % p.tiles_w, t2 = tile / p.tiles_w;
       const int th = t2 % p.tiles_h, n = t2 / p.tiles_h;
+      int nt = 2 * (pi + nclusters) + (int)rank;  // this CTA's next tile: pull its boxes into L2 now
+      const bool has_next = nt < p.total_tiles;
+      if (!has_next) nt = tile;
+      const int ntw = nt % p.tiles_w, nt2 = nt / p.tiles_w;
+      const int nth = nt2 % p.tiles_h, nn = nt2 / p.tiles_h;
       for (int cc = 0; cc < 2; ++cc) {
         mbar_wait(&empty[stage], phase ^ 1u);
         if (elect_one()) {
-          if (leader) mbar_expect_tx(&full[stage], 2u * (uint32_t)A_STAGE);
+          if (leader) mbar_expect_tx(&full[stage], 2u * (uint32_t)A_BYTES);
           tma2_load_4d(tiles + stage * A_STAGE, &tm_x, &full[stage], cc * 64, tw * TC - 1, th * TR - 1, n);
+          if (has_next) tma_prefetch_4d(&tm_x, cc * 64, ntw * TC - 1, nth * TR - 1, nn);
         }
         __syncwarp();
         if (++stage == NSTAGE) {
@@ -150,11 +191,9 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const int ky = tap / 3, kx = tap % 3;  // input pixel (r + ky, c + kx) of the halo tile
-              // row group g = output row r: 8 pixels x 128 B, groups PITCH x 128 B apart; the first row of every
-              // group sits kx rows into its 1024-byte swizzle period -> base offset kx
+              // row group g = output row r: 8 pixels x 128 B, groups PITCH x 128 B apart
               const uint64_t a_desc = make_smem_desc(sa + (uint32_t)((ky * PITCH + kx) * 128), 16, PITCH * 128,
-                                                     LAYOUT_SW128) |
-                                      ((uint64_t)(p.base_offset_mode ? kx : 0) << 49);
+                                                     LAYOUT_SW128);
               const uint64_t b_desc = make_smem_desc(w_base + (uint32_t)((tap * 2 + cc) * W_SLAB), 16, 1024, LAYOUT_SW128);
 #pragma unroll
               for (int k = 0; k < 4; ++k) umma2_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (cc | tap | k) ? 1u : 0u);
@@ -173,11 +212,14 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     }
   } else {
     // ------------------------------------------------------------ epilogue warps 2..9 (both CTAs, own TMEM)
-    // Two warps per TMEM lane quarter, 64 output channels each; thread = pixel m = q * 32 + lane = (r, c).
+    // Two warps per TMEM lane quarter, 64 output channels each; thread = pixel m = q * 32 + lane = (r, c), i.e. the
+    // warp's 32 pixels are rows 4q..4q+3 of the tile.  Staging block: pixel p at p * 128 B, its 16-byte piece j at
+    // ((j ^ (p & 7)) * 16) -- the 128-byte-swizzle layout of a (64 ch, 8 px, 4 rows) TMA box.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int row = q * 32 + lane;
-    const int rl = row >> 3, cl = row & 7;
+    const uint32_t my_stg = smem_u32(stg + (warp - 2) * STG_WARP);
+    const uint32_t my_row = my_stg + (uint32_t)lane * 128u;   // this thread's pixel in the staging block
+    const int sw = lane & 7;
     int it = 0;
     for (int pi = cid; pi < pairs; pi += nclusters, ++it) {
       const int acc = it & 1;
@@ -186,18 +228,33 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       const int tcl = tvalid ? tile : p.total_tiles - 1;
       const int tw = tcl % p.tiles_w, t2 = tcl / p.tiles_w;
       const int th = t2 % p.tiles_h, n = t2 / p.tiles_h;
-      const int oy = th * TR + rl, ox = tw * TC + cl;
-      const bool valid = tvalid && oy < p.OH && ox < p.OW;
-      const size_t off = (((size_t)n * p.OH + oy) * p.OW + ox) * 128 + half * 64;
-      // residual channels of this pixel, fetched while the tile's MMAs are in flight
+      const int oy0 = th * TR + q * 4, ox0 = tw * TC;
+      // the previous tile's TMA store must have finished READING the staging block
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+      // residual channels of the warp's pixels: cp.async, 4 pixels x 128 contiguous bytes per instruction, fetched
+      // while the tile's MMAs are still in flight; then every thread reads its own pixel back (conflict-free)
       uint4 R1[8], R2[8];
-      if (p.r1 && valid) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) R1[j] = ld_nc16(p.r1 + off + j * 8);
-      }
-      if (p.r2 && valid) {
+      for (int rr = 0; rr < 2; ++rr) {
+        const __half* rsrc = rr == 0 ? p.r1 : p.r2;
+        if (rsrc == nullptr) continue;  // warp-uniform
 #pragma unroll
-        for (int j = 0; j < 8; ++j) R2[j] = ld_nc16(p.r2 + off + j * 8);
+        for (int i = 0; i < 8; ++i) {
+          const int pp = 4 * i + (lane >> 3), j = lane & 7;  // pixel of the block, 16-byte piece
+          const int oy = oy0 + (pp >> 3), ox = ox0 + (pp & 7);
+          const bool ok = tvalid && oy < p.OH && ox < p.OW;
+          const size_t goff = ok ? ((((size_t)n * p.OH + oy) * p.OW + ox) * 128 + half * 64 + j * 8) : 0;
+          cp_async16(my_stg + (uint32_t)(pp * 128 + ((j ^ (pp & 7)) << 4)), rsrc + goff, ok);
+        }
+        cp_async_wait_all();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 v = lds16(my_row + (uint32_t)((j ^ sw) << 4));
+          if (rr == 0) R1[j] = v; else R2[j] = v;
+        }
+        __syncwarp();  // everyone has read before the block is overwritten
       }
       mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u);
       fence_after_sync();
@@ -208,35 +265,39 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         uint32_t v[16];
         tmem_ld_32x16(lane_base + (uint32_t)(chunk * 16), v);
         tmem_ld_wait();
-        if (valid) {
-          float f[16];
+        float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float t = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), s_scale[c0 + j]), s_shift[c0 + j]);
-            f[j] = p.act == DSIN_ACT_RELU ? fmaxf(t, 0.f) : t;
-          }
-          if (p.r1) {
-            add_half8(f, R1[2 * chunk]);
-            add_half8(f + 8, R1[2 * chunk + 1]);
-          }
-          if (p.r2) {
-            add_half8(f, R2[2 * chunk]);
-            add_half8(f + 8, R2[2 * chunk + 1]);
-          }
+        for (int j = 0; j < 16; ++j) {
+          float t = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), s_scale[c0 + j]), s_shift[c0 + j]);
+          f[j] = p.act == DSIN_ACT_RELU ? fmaxf(t, 0.f) : t;
+        }
+        if (p.r1) {
+          add_half8(f, R1[2 * chunk]);
+          add_half8(f + 8, R1[2 * chunk + 1]);
+        }
+        if (p.r2) {
+          add_half8(f, R2[2 * chunk]);
+          add_half8(f + 8, R2[2 * chunk + 1]);
+        }
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint4 uh;
-            __half2* hh = reinterpret_cast<__half2*>(&uh);
+        for (int g = 0; g < 2; ++g) {
+          uint4 uh;
+          __half2* hh = reinterpret_cast<__half2*>(&uh);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) hh[e] = __floats2half2_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
-            reinterpret_cast<uint4*>(p.y + off + chunk * 16)[g] = uh;
-          }
+          for (int e = 0; e < 4; ++e) hh[e] = __floats2half2_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
+          sts16(my_row + (uint32_t)(((2 * chunk + g) ^ sw) << 4), uh);
         }
       }
+      // accumulator drained: hand it back before the (asynchronous) store
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty[acc], 0);  // the leader's accumulator-empty barrier
+      fence_proxy_async();  // generic-proxy writes to the staging block -> visible to the TMA store
+      __syncwarp();
+      if (lane == 0 && tvalid) tma_store_4d(&tm_y, my_stg, half * 64, ox0, oy0, n);  // clips rows / pixels past the image
     }
+    if (lane == 0) tma_store_wait_all();  // global writes complete before the kernel ends
+    __syncwarp();
   }
 
   __syncthreads();
@@ -250,15 +311,17 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 }  // namespace
 
 int conv_ws_launch(dsin_handle_t h, const __half* x, const __half* w_packed, const ConvWsArgs& a, cudaStream_t st) {
-  CUtensorMap tx, tw;
+  CUtensorMap tx, tw, ty;
   const uint64_t xd[4] = {128, (uint64_t)a.OW, (uint64_t)a.OH, (uint64_t)a.n};
   const uint64_t xs[3] = {256, (uint64_t)a.OW * 256, (uint64_t)a.OH * a.OW * 256};
   const uint32_t xb[4] = {64, PITCH, HALO_R, 1};
+  const uint32_t yb[4] = {64, TC, 4, 1};  // one epilogue warp's block: 64 channels x 8 pixels x 4 rows
   const uint64_t wd[2] = {128, 9 * 128};
   const uint64_t wsb[1] = {256};
   const uint32_t wb[2] = {64, 64};
   if (!encode_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x, xd, xs, xb, CU_TENSOR_MAP_SWIZZLE_128B) ||
-      !encode_tmap(&tw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w_packed, wd, wsb, wb, CU_TENSOR_MAP_SWIZZLE_128B))
+      !encode_tmap(&tw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w_packed, wd, wsb, wb, CU_TENSOR_MAP_SWIZZLE_128B) ||
+      !encode_tmap(&ty, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.y, xd, xs, yb, CU_TENSOR_MAP_SWIZZLE_128B))
     return dsin_fail(h, DSIN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", __func__);
   static bool configured[DSIN_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
   if (!configured[h->device]) {
@@ -273,7 +336,7 @@ int conv_ws_launch(dsin_handle_t h, const __half* x, const __half* w_packed, con
   const int pairs = (p.total_tiles + 1) / 2;
   int clusters = h->sm_count / 2;
   if (clusters > pairs) clusters = pairs;
-  conv_ws_kernel<<<2 * clusters, 320, SMEM_BYTES, st>>>(tx, tw, p);
+  conv_ws_kernel<<<2 * clusters, 320, SMEM_BYTES, st>>>(tx, tw, ty, p);
   DSIN_LAUNCHED(h);
   return DSIN_OK;
 }

@@ -349,11 +349,8 @@ __global__ void sif_rescore_kernel(const float2* __restrict__ cand, int ncand, c
   const float* qp = q + wid * kdim;
   const float* ps = pstat + wid * 4;
   unsigned long long key = 0ull;
-  for (int c = 0; c < ncand; ++c) {
-    const float2 cv = cp[c];
-    const int idx = __float_as_int(cv.y);
-    if (!(cv.x >= thr) || idx < 0) continue;  // warp-uniform
-    const int i = idx / wp, j = idx % wp;
+  // exact masked score of position (i, j): fp32 data, fp64 dot product, the reference's literal fp32 algebra
+  auto rescore = [&](int i, int j) {
     const float* rp = r + (((int64_t)img * hh + i) * ww + j) * 3;
     double acc = 0.0;
     for (int k = lane; k < kdim; k += 32) {
@@ -365,9 +362,32 @@ __global__ void sif_rescore_kernel(const float2* __restrict__ cand, int ncand, c
       const float4 ys = reinterpret_cast<const float4*>(ystat)[((int64_t)img * hp + i) * wp + j];
       float s = sif_pearson((float)acc, ys.x, ys.y, ys.z, ps[0], ps[2], ps[3], (float)kdim);
       if (use_mask) s = __fmul_rn(s, sif_mask_exact(pch, i, j, hh, ww, ph, pw));
-      const unsigned long long k2 = sif_pack(s, (unsigned)idx);
+      const unsigned long long k2 = sif_pack(s, (unsigned)(i * wp + j));
       key = k2 > key ? k2 : key;
     }
+  };
+  if (ps[3] < 0.f) {  // den_x < 0 (a flat patch whose fp32 variance rounded below zero): sqrt(den) is NaN at every
+    if (lane == 0) keys[wid] = 0ull;  // position, a NaN never wins tf.argmax, all-NaN -> index 0 (sif_common.cuh)
+    return;
+  }
+  for (int c = 0; c < ncand; ++c) {
+    const float2 cv = cp[c];
+    const int idx = __float_as_int(cv.y);
+    if (!(cv.x >= thr) || idx < 0) continue;  // warp-uniform
+    rescore(idx / wp, idx % wp);
+  }
+  // Overflow: a (work unit, column half) keeps only its TOPK best coarse scores.  If even the weakest kept one is
+  // within DELTA of the global coarse best, positions that were NOT kept may qualify too (periodic textures, flat
+  // regions: many near-equal scores) -- then every position of that group is rescored exactly.  Rare; costs
+  // ~0.3 ms per group and patch when it happens.
+  for (int g = 0; g < ncand / TOPK; ++g) {
+    const float2 weakest = cp[g * TOPK + TOPK - 1];
+    if (!(weakest.x >= thr) || __float_as_int(weakest.y) < 0) continue;  // warp-uniform
+    const int rg = g >> 1, half = g & 1;
+    const int i1 = min(hp, (rg + 1) * ROWS_PER_UNIT);
+    for (int i = rg * ROWS_PER_UNIT; i < i1; ++i)
+      for (int j = 0; j < wp; ++j)
+        if (((j & (TN - 1)) >> 7) == half) rescore(i, j);
   }
   if (lane == 0) keys[wid] = key;
 }

@@ -224,7 +224,6 @@ Conv3x3TC = ConvTC
 CONV_PAIR_SHARED = 1
 CONV_NO_CTA_PAIR = 2             # cross-check: one-CTA kernel for a 128->128 layer
 CONV_NO_WEIGHT_STATIONARY = 4    # cross-check: tap-streaming CTA-pair kernel for a terms = 1 trunk layer
-CONV_WS_NO_BASE_OFFSET = 8       # diagnostic
 
 
 class _PairDesc(object):

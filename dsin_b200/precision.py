@@ -11,8 +11,11 @@ Which passes of AE.siNet_get_reconstructed (/root/reference/src/AE.py:132-148) n
   * decoder(y), decoder(x) and the SI-Net produce float images only (gate: |d MS-SSIM| <= 1e-4).
   * the probability model produces bits (gate: |d bpp| <= 1e-5): 3-term.
 
-The shipped policy is the fastest one that passes tests/test_gpu_parity.py::test_precision_policy_*; the
-measurements behind the choice are in DESIGN.md section 5 and profiles/r2_*precision*.json.
+Measured on 320x1224 pairs against the oracle (tools/precision_probe.py, profiles/r2_precision_probe.json):
+  decoders on fp16 operands  : x_dec moves by 0.07 grey levels rms (0.7 max); |d MS-SSIM| stays at the 1e-5 level
+  SI-Net on fp16 operands    : MS-SSIM drops by ~1e-4 on every image (nine layers, errors add up)  -> stays 3-term
+  encoder(y) on fp16 operands: ~100 symbols of y flip per image -> y_dec changes discretely        -> stays 3-term
+The shipped policy is therefore DEC1; tests/test_gpu_freerun.py holds it to the north_star tolerances.
 """
 from __future__ import annotations
 
@@ -30,7 +33,7 @@ SINET1 = Policy("sinet1", 3, 3, 3, 1, 3)           # only the SI-Net on fp16 ope
 
 BY_NAME = {p.name: p for p in (EXACT, MIXED, MIXED_Y1, FAST, DEC1, SINET1)}
 
-DEFAULT = EXACT
+DEFAULT = DEC1
 
 
 def get(policy):

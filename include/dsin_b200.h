@@ -82,9 +82,9 @@ typedef struct {
 } dsin_conv_desc_t;
 enum { DSIN_CONV_PAIR_SHARED = 1,
        DSIN_CONV_NO_CTA_PAIR = 2, /* run a 128->128 layer on the one-CTA kernel (cross-check of the CTA-pair kernels) */
-       DSIN_CONV_NO_WEIGHT_STATIONARY = 4, /* terms = 1, 3x3 128->128: use the tap-streaming CTA-pair kernel instead of
+       DSIN_CONV_NO_WEIGHT_STATIONARY = 4 /* terms = 1, 3x3 128->128: use the tap-streaming CTA-pair kernel instead of
                                               the weight-stationary halo-tile kernel (cross-check) */
-       DSIN_CONV_WS_NO_BASE_OFFSET = 8 /* diagnostic: leave the shared-memory descriptor's base-offset field 0 */ };
+};
 int dsin_conv2d(dsin_handle_t h, const dsin_conv_desc_t* d, const float* x, const float* w,
                 const float* scale, const float* shift, const float* res1, const float* res2,
                 float* y, void* stream);

@@ -159,7 +159,9 @@ def quantize(z, centers):
 # --------------------------------------------------------------------------------------
 # encoder / decoder (src/autoencoder_imgcomp.py:219-269)
 # --------------------------------------------------------------------------------------
-def encode(x, W, B=5, trace=None):
+def encode(x, W, B=5, trace=None, force_symbols=None):
+    """force_symbols (test helper): int tensor (N,C,h,w); where it is >= 0 the quantiser's decision is overridden
+    by it (qhard, qbar follow).  Used to replay the oracle downstream of an adjudicated near-tie."""
     net = normalize(x)
     net = conv_block(net, W, ENC + "h1", stride=2, trace=trace)
     net = conv_block(net, W, ENC + "h2", stride=2, trace=trace)
@@ -174,7 +176,12 @@ def encode(x, W, B=5, trace=None):
     z33 = conv_block(net, W, ENC + "to_bn", stride=2, relu=False, trace=trace)
     hm = heatmap3d(z33)
     z = hm * z33[:, 1:]
-    qbar, _qsoft, qhard, symbols = quantize(z, W[ENC + "centers"])
+    qbar, qsoft, qhard, symbols = quantize(z, W[ENC + "centers"])
+    if force_symbols is not None:
+        fs = torch.as_tensor(force_symbols).to(torch.int64)
+        symbols = torch.where(fs >= 0, fs, symbols)
+        qhard = _t(W[ENC + "centers"], z.dtype)[symbols]
+        qbar = qsoft + (qhard - qsoft)
     return EncoderOutput(qbar, qhard, symbols, z, hm)
 
 
@@ -391,20 +398,25 @@ def crop_and_resize_patches(y_hwc, rows, cols, ph, pw):
     return out
 
 
-def si_finder(x_patches, y_hwc, mask, ph, pw, y_dec_hwc):
-    """src/siFinder.py:7-53 (Pearson branch, batch_size == 1)."""
+def si_finder(x_patches, y_hwc, mask, ph, pw, y_dec_hwc, force_rowcol=None):
+    """src/siFinder.py:7-53 (Pearson branch, batch_size == 1).  force_rowcol (test helper): (row, col) int arrays,
+    entries >= 0 override the argmax (replay downstream of an adjudicated near-tie)."""
     q = rgb_transform(sif_normalize_nhwc(x_patches))
     r = rgb_transform(sif_normalize_nhwc(y_dec_hwc))
     idx, best = pearson_scores(q, r, mask)
     ncc_w = y_dec_hwc.shape[1] - pw + 1
     row = (idx // ncc_w).to(torch.int32)
     col = (idx % ncc_w).to(torch.int32)
+    if force_rowcol is not None:
+        fr, fc = (torch.as_tensor(np.asarray(a)).to(torch.int32) for a in force_rowcol)
+        row = torch.where(fr >= 0, fr, row)
+        col = torch.where(fc >= 0, fc, col)
     y_np = y_hwc.to(torch.float32).numpy()
     yp = crop_and_resize_patches(y_np, row.numpy(), col.numpy(), ph, pw)
     return torch.from_numpy(yp).to(x_patches.dtype), best, q, r, row, col
 
 
-def si_full_img(x_dec, y, y_dec, ph=20, pw=24, use_mask=True):
+def si_full_img(x_dec, y, y_dec, ph=20, pw=24, use_mask=True, force_rowcol=None):
     """src/siFull_img.py:5-42: returns y_syn NCHW plus (row, col, best) per image."""
     N, C, H, W = x_dec.shape
     mask = gaussian_masks(H, W, ph, pw) if use_mask else None
@@ -414,7 +426,8 @@ def si_full_img(x_dec, y, y_dec, ph=20, pw=24, use_mask=True):
         yi = y[n].permute(1, 2, 0)
         ydi = y_dec[n].permute(1, 2, 0)
         xp = extract_patches(xi, ph, pw)
-        yp, best, _q, _r, row, col = si_finder(xp, yi, mask, ph, pw, ydi)
+        frc = None if force_rowcol is None else (force_rowcol[0][n], force_rowcol[1][n])
+        yp, best, _q, _r, row, col = si_finder(xp, yi, mask, ph, pw, ydi, frc)
         outs.append(fold_patches(yp, H, W).permute(2, 0, 1))
         rows.append(row)
         cols.append(col)
@@ -445,23 +458,25 @@ Reconstruction = namedtuple(
     "Reconstruction", ["y_dec", "y_syn", "x_dec", "x_with_si", "bpp", "symbols", "row", "col", "bits_per_image", "best"])
 
 
-def ae_pass(x, W):
-    enc = encode(x, W)
+def ae_pass(x, W, force_symbols=None):
+    enc = encode(x, W, force_symbols=force_symbols)
     return enc, decode(enc.qbar, W)
 
 
-def reconstruct(x_np, y_np, W, dtype=torch.float32, ph=20, pw=24, use_mask=True):
+def reconstruct(x_np, y_np, W, dtype=torch.float32, ph=20, pw=24, use_mask=True, force_symbols_x=None,
+                force_symbols_y=None, force_rowcol=None):
     """x_np, y_np: (N,3,H,W) uint8-valued arrays.  Each pair is processed with the
-    reference's batch-1 semantics; bpp is the batch aggregate (src/bits_imgcomp.py:13-14)."""
+    reference's batch-1 semantics; bpp is the batch aggregate (src/bits_imgcomp.py:13-14).
+    force_*: test helpers that override quantiser / argmax decisions at adjudicated near-ties (entries >= 0)."""
     x = _t(x_np, dtype)
     y = _t(y_np, dtype)
     N, _, H, Wd = x.shape
     with torch.no_grad():
-        _ency, y_dec = ae_pass(y, W)  # create_y_dec, src/AE.py:150-152
-        encx, x_dec = ae_pass(x, W)
+        _ency, y_dec = ae_pass(y, W, force_symbols_y)  # create_y_dec, src/AE.py:150-152
+        encx, x_dec = ae_pass(x, W, force_symbols_x)
         bits = probclass_bitcost(encx.qbar, encx.symbols, W)
         bpp = bitcost_to_bpp(bits, N * H * Wd)
-        y_syn, row, col, best = si_full_img(x_dec, y, y_dec, ph, pw, use_mask)
+        y_syn, row, col, best = si_full_img(x_dec, y, y_dec, ph, pw, use_mask, force_rowcol)
         cat = torch.cat([normalize(x_dec), normalize(y_syn)], dim=1)
         x_with_si = denormalize(si_net(cat, W))
     return Reconstruction(y_dec, y_syn, x_dec, x_with_si, bpp, encx.symbols, row, col,

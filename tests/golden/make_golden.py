@@ -12,6 +12,15 @@ Run here (needs /root/reference):  python tests/golden/make_golden.py
                         helpers (:371-393), AE.normalize / denormalize / get_mean_var (src/AE.py:222-250), and the
                         host helpers readfiles (src/DataProvider.py:96-100), l1_x_vs_rec and save_test_imgs_fn
                         (src/utils.py:82-111).
+  * tf_pieces_golden.npz - reference functions whose bodies are elementwise / shape TensorFlow ops only, extracted with
+                        ``ast`` and executed under a small numpy stand-in for those ops (``_make_tf`` / ``_T`` below: tile,
+                        expand_dims, split, concat, sigmoid, softmax, argmax, one_hot, reduce_sum, ... each following the
+                        op's documented semantics in float32): reduce_mean_and_std_normalize_images and rgb_transform
+                        (src/siFinder.py:56-73,138-154), _get_heatmap3D and _mask_with_heatmap
+                        (src/autoencoder_imgcomp.py:173-201), _quantize1d and phi_times_centers
+                        (src/quantizer_imgcomp.py:43-100), bitcost_to_bpp (src/bits_imgcomp.py:4-20).  This pins which
+                        channels / constants / formulas the reference's own code applies; the convolution-type ops
+                        (Conv2D, Conv3D, CropAndResize, ExtractImagePatches) have no stand-in and stay unpinned.
 Nothing from the reference is copied into the repo; only its numeric outputs are stored.
 """
 import ast
@@ -144,9 +153,152 @@ def make_model_pieces():
     np.savez_compressed(os.path.join(OUT, "model_pieces_golden.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# numpy stand-in for the elementwise / shape TensorFlow ops the extracted functions use
+# ------------------------------------------------------------------------------------------------------------------
+class _Shape(tuple):
+    @property
+    def ndims(self):
+        return len(self)
+
+    def as_list(self):
+        return list(self)
+
+
+class _DType(object):
+    def __init__(self, np_dtype):
+        self.np_dtype = np.dtype(np_dtype)
+
+    def is_compatible_with(self, other):
+        return np.dtype(getattr(other, "np_dtype", other)) == self.np_dtype
+
+
+def _raw(v):
+    return v.a if isinstance(v, _T) else v
+
+
+class _T(object):
+    """A 'tensor': numpy array + the attribute surface the reference code touches."""
+
+    def __init__(self, a):
+        self.a = np.asarray(_raw(a))
+
+    shape = property(lambda self: _Shape(self.a.shape))
+    dtype = property(lambda self: _DType(self.a.dtype))
+
+    def get_shape(self):
+        return self.shape
+
+    def __getitem__(self, idx):
+        return _T(self.a[idx])
+
+    def __len__(self):
+        return len(self.a)
+
+    def __int__(self):
+        return int(self.a)
+
+    def __index__(self):
+        return int(self.a)
+
+    def __format__(self, spec):
+        return format(str(self.a.shape), spec)
+
+
+for _name, _fn in (("add", np.add), ("sub", np.subtract), ("mul", np.multiply), ("truediv", np.true_divide)):
+    setattr(_T, "__%s__" % _name, (lambda f: lambda self, o: _T(f(self.a, _raw(o))))(_fn))
+    setattr(_T, "__r%s__" % _name, (lambda f: lambda self, o: _T(f(_raw(o), self.a)))(_fn))
+_T.__neg__ = lambda self: _T(-self.a)
+
+
+def _softmax(v, axis=-1):
+    a = _raw(v)
+    e = np.exp(a - a.max(axis=axis, keepdims=True))
+    return _T((e / e.sum(axis=axis, keepdims=True)).astype(a.dtype))
+
+
+def _one_hot(idx, depth, axis=-1, dtype=None):
+    i = _raw(idx)
+    return _T((np.arange(depth) == i[..., None]).astype(np.float32))
+
+
+def _make_tf():
+    import contextlib
+    f32 = np.float32
+    nn = types.SimpleNamespace(sigmoid=lambda v: _T((f32(1) / (f32(1) + np.exp(-_raw(v)))).astype(f32)), softmax=_softmax)
+    return types.SimpleNamespace(
+        float32=_DType(np.float32), nn=nn, name_scope=lambda *_a, **_k: contextlib.nullcontext(),
+        tile=lambda v, reps: _T(np.tile(np.asarray(_raw(v), dtype=np.float32), reps)),
+        expand_dims=lambda v, axis: _T(np.expand_dims(_raw(v), axis)),
+        divide=lambda a, b: _T(np.true_divide(_raw(a), _raw(b))),
+        split=lambda v, sizes, axis: [_T(p) for p in np.split(_raw(v), np.cumsum(sizes)[:-1], axis=axis)],
+        concat=lambda vs, axis: _T(np.concatenate([_raw(v) for v in vs], axis=axis)),
+        clip_by_value=lambda v, lo, hi: _T(np.clip(_raw(v), lo, hi)),
+        range=lambda n, dtype=None: _T(np.arange(n, dtype=np.float32)),
+        reshape=lambda v, shp: _T(np.reshape(_raw(v), [int(_raw(s_)) for s_ in _raw(shp)])),
+        maximum=lambda a, b, name=None: _T(np.maximum(_raw(a), _raw(b)).astype(np.float32)),
+        minimum=lambda a, b, name=None: _T(np.minimum(_raw(a), _raw(b)).astype(np.float32)),
+        shape=lambda v: _T(np.array(_raw(v).shape, dtype=np.int32)),
+        square=lambda v: _T(np.square(_raw(v))), abs=lambda v: _T(np.abs(_raw(v))),
+        argmax=lambda v, axis: _T(np.argmax(_raw(v), axis=axis).astype(np.int64)),
+        one_hot=_one_hot,
+        reduce_sum=lambda v, axis=None, name=None: _T(np.sum(_raw(v), axis=axis, dtype=np.float32)),
+        reduce_prod=lambda v: _T(np.prod(_raw(v))),
+        to_float=lambda v: _T(np.float32(_raw(v))),
+    )
+
+
+def _extract_tf(path, names, consts=()):
+    """Like _extract, for functions that call tf ops: runs them against the numpy stand-in."""
+    tree = ast.parse(open(os.path.join(REF, path)).read())
+    body = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name in names]
+    body += [n for n in tree.body if isinstance(n, ast.Assign) and any(getattr(t, "id", None) in consts for t in n.targets)]
+    for n in body:
+        if isinstance(n, ast.FunctionDef):
+            n.decorator_list = []
+    ns = {"np": np, "tf": _make_tf()}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
+def make_tf_pieces():
+    rng = np.random.default_rng(23)
+    out = {}
+    cfg = types.SimpleNamespace(use_L2andLAB=False)
+    sf = _extract_tf("siFinder.py", {"reduce_mean_and_std_normalize_images", "rgb_transform"})
+    img = rng.integers(0, 256, size=(5, 20, 24, 3)).astype(np.float32)  # patches, channel last
+    out["sif_in"] = img
+    norm = sf["reduce_mean_and_std_normalize_images"](_T(img), cfg)
+    out["sif_norm"] = norm.a
+    out["sif_rgb"] = sf["rgb_transform"](norm, cfg).a
+    ae = _extract_tf("autoencoder_imgcomp.py", {"_get_heatmap3D", "_mask_with_heatmap"})
+    z33 = (1.5 * rng.standard_normal((2, 33, 6, 7))).astype(np.float32)
+    z33[0, 0, :2] = -30.0
+    z33[1, 0, 2:4] = 30.0
+    out["z33"] = z33
+    hm = ae["_get_heatmap3D"](_T(z33))
+    out["heatmap3d"] = hm.a
+    out["z_masked"] = ae["_mask_with_heatmap"](_T(z33), hm).a
+    qz = _extract_tf("quantizer_imgcomp.py", {"_quantize1d", "phi_times_centers"}, consts=("_HARD_SIGMA",))
+    centers = np.array([0.55, -0.92, -1.84, -1.93, 1.25, 1.65], dtype=np.float32)
+    x = out["z_masked"].copy()
+    x[0, 0, 0, :6] = centers          # exactly on a centre
+    x[0, 1, 0, 0] = np.float32(0.5 * (centers[2] + centers[3]))  # midway between the two closest centres
+    out["q_in"], out["q_centers"] = x, centers
+    qsoft, qhard, sym = qz["_quantize1d"](_T(x), _T(centers), 1, "NCHW")
+    out["q_soft"], out["q_hard"], out["q_symbols"] = qsoft.a, qhard.a, sym.a
+    bits = _extract_tf("bits_imgcomp.py", {"bitcost_to_bpp", "num_pixels_in_input_batch"})
+    bc = rng.uniform(0, 4, size=(2, 32, 5, 9)).astype(np.float32)
+    inp = np.zeros((2, 3, 40, 72), np.float32)
+    out["bc"], out["bc_input_shape"] = bc, np.array(inp.shape)
+    out["bpp"] = np.float32(bits["bitcost_to_bpp"](_T(bc), _T(inp)).a)
+    np.savez_compressed(os.path.join(OUT, "tf_pieces_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     make_masks()
     make_msssim()
     make_model_pieces()
-    for f in ("mask_golden.npz", "msssim_golden.npz", "model_pieces_golden.npz"):
+    make_tf_pieces()
+    for f in ("mask_golden.npz", "msssim_golden.npz", "model_pieces_golden.npz", "tf_pieces_golden.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -43,7 +43,7 @@ def _ref64(tcl, w, scale, shift, xh, res, act):
     return y
 
 
-@pytest.mark.parametrize("shape", [(2, 20, 36), (1, 80, 306), (3, 9, 17), (1, 16, 8), (2, 33, 70)])
+@pytest.mark.parametrize("shape", [(2, 20, 36), (1, 80, 306), (3, 9, 17), (1, 16, 24), (2, 33, 70)])
 @pytest.mark.parametrize("nres", [0, 1, 2])
 def test_conv_ws_matches_float64_and_streaming_kernel(shape, nres):
     n, hh, ww = shape

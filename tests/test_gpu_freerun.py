@@ -1,0 +1,145 @@
+"""Free-running parity of the public call at the BASELINE geometry, batch 8 (configs[1]) and batch 1, under the
+SHIPPED precision policy, with every tolerance of north_star applied without slack:
+
+  * symbols of x (the transmitted integers) equal the oracle's except at float64-adjudicated near-ties: the two
+    nearest quantiser centres are equidistant from the float64 z to within SYMBOL_MARGIN (the measured error
+    bound of the tensor-core arithmetic);
+  * the ORACLE is then replayed with exactly those tie-breaks forced (oracle.reconstruct(force_symbols_*)), and
+    against that replay:  |d bpp| <= 1e-5,  (row, col) equal except float64-adjudicated near-ties of the score
+    (which are forced in turn),  |d MS-SSIM| <= 1e-4 in both call forms, per image.
+No tolerance is scaled by the number of mismatches."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dsin_oracle as O
+from oracle import ms_ssim_oracle as M
+
+import oracle_cache
+from parity_utils import make_ae
+
+pytestmark = pytest.mark.gpu
+
+SYMBOL_MARGIN = 6e-4   # float64 |d1 - d2| below which the fp32-class GPU path may pick the other centre
+ROWCOL_GAP = 5e-4      # float64 score gap below which the argmax may pick the other position: the shipped policy
+                       # decodes x_dec / y_dec with fp16 operands (0.07 grey levels rms), which moves a masked Pearson
+                       # score by up to ~2e-4; a flip is accepted only between positions at least this close
+
+
+def _forced(gpu_sym, ref_sym, margin64, what):
+    """-> force array (-1 = keep the oracle's decision), after checking every difference is a near-tie."""
+    gpu_sym, ref_sym = np.asarray(gpu_sym, np.int64), np.asarray(ref_sym, np.int64)
+    mism = gpu_sym != ref_sym
+    n = int(mism.sum())
+    if n:
+        worst = float(margin64[mism].max())
+        print("%s: %d / %d symbols differ from the fp32 oracle; float64 margins up to %.2e" % (what, n, mism.size, worst))
+        assert worst < SYMBOL_MARGIN, (what, worst)
+    assert n <= max(2, mism.size // 25000), (what, n)
+    return np.where(mism, gpu_sym, -1), n
+
+
+def _score64(q64, r64, mask, p, row, col):
+    return O.score_at(q64, r64, mask, p, int(row), int(col))
+
+
+def _adjudicate_rowcol(ref, row, col, H, W):
+    """(row, col) differences between the GPU and the replayed oracle must be float64 near-ties of the masked score
+    evaluated on the ORACLE's decoded images; returns force arrays for a second replay."""
+    row, col = np.asarray(row), np.asarray(col)
+    rr, rc = ref.row.numpy(), ref.col.numpy()
+    mism = (row != rr) | (col != rc)
+    if int(mism.sum()):
+        mask = O.gaussian_masks(H, W, 20, 24)
+        for n, p in zip(*np.nonzero(mism)):
+            xi = ref.x_dec[n].double().permute(1, 2, 0)
+            yi = ref.y_dec[n].double().permute(1, 2, 0)
+            q64 = O.rgb_transform(O.sif_normalize_nhwc(O.extract_patches(xi, 20, 24)))
+            r64 = O.rgb_transform(O.sif_normalize_nhwc(yi))
+            a = _score64(q64, r64, mask, p, row[n, p], col[n, p])
+            b = _score64(q64, r64, mask, p, rr[n, p], rc[n, p])
+            assert abs(a - b) < ROWCOL_GAP, (n, p, a, b)
+    assert int(mism.sum()) <= max(1, mism.size // 400), int(mism.sum())
+    return np.where(mism, row, -1), np.where(mism, col, -1), int(mism.sum())
+
+
+def _run(case_name):
+    Wt, d = oracle_cache.get(case_name)
+    c = oracle_cache.CASES[case_name]
+    H, W, B = c["H"], c["W"], c["B"]
+    ae = make_ae(H, W, Wt)  # shipped precision policy
+    x, y = d["x"], d["y"]
+    y_dec, y_syn, x_dec, x_with_si, bpp = [np.array(a) for a in ae.siNet_get_reconstructed(x, y)]
+    sym_x = ae.last["symbols"].cpu().numpy()
+    sym_y = ae.last["symbols_y"].cpu().numpy()
+    row, col = ae.last["row"].cpu().numpy(), ae.last["col"].cpu().numpy()
+    bits_gpu = ae.last["bits_sum"].cpu().numpy()
+
+    fx, nx = _forced(sym_x, d["sym32_x"], d["margin64_x"], "x")
+    fy, ny = _forced(sym_y, d["sym32_y"], d["margin64_y"], "y")
+    assert np.array_equal(d["sym32_x"], d["ref_symbols"])
+
+    # replay the oracle downstream of the adjudicated tie-breaks (only the images that have one)
+    xf, yf = x.astype(np.float32), y.astype(np.float32)
+    affected = [n for n in range(B) if (fx[n] >= 0).any() or (fy[n] >= 0).any()]
+    ref_bits = d["ref_bits_per_image"].copy()
+    ref_row, ref_col = d["ref_row"].copy(), d["ref_col"].copy()
+    ref_ms = {n: (float(d["ref_msssim_std"][n]), float(d["ref_msssim_call"][n])) for n in range(B)}
+    replay = {}
+    for n in affected:
+        r = O.reconstruct(xf[n:n + 1], yf[n:n + 1], Wt, force_symbols_x=torch.as_tensor(fx[n:n + 1]),
+                          force_symbols_y=torch.as_tensor(fy[n:n + 1]))
+        replay[n] = r
+        ref_bits[n] = float(r.bits_per_image[0])
+        ref_row[n], ref_col[n] = r.row[0].numpy(), r.col[0].numpy()
+
+    # ---- bpp: the batch aggregate (src/bits_imgcomp.py:13-14) and per image
+    bpp_ref = float(ref_bits.sum()) / (B * H * W)
+    print("%s: bpp gpu %.7f oracle(replayed) %.7f; symbol tie-breaks x %d y %d" % (case_name, float(bpp), bpp_ref, nx, ny))
+    assert abs(float(bpp) - bpp_ref) <= 1e-5
+    assert np.abs(bits_gpu - ref_bits).max() / (H * W) <= 1e-5
+
+    # ---- (row, col): near-ties of the score are adjudicated on the replayed oracle's images and forced
+    n_rc = 0
+    for n in range(B):
+        mism = (row[n] != ref_row[n]) | (col[n] != ref_col[n])
+        if not mism.any():
+            continue
+        r = replay.get(n)
+        if r is None:
+            r = O.reconstruct(xf[n:n + 1], yf[n:n + 1], Wt)
+        fr, fc, k = _adjudicate_rowcol(r, row[n:n + 1], col[n:n + 1], H, W)
+        n_rc += k
+        replay[n] = O.reconstruct(xf[n:n + 1], yf[n:n + 1], Wt, force_symbols_x=torch.as_tensor(fx[n:n + 1]),
+                                  force_symbols_y=torch.as_tensor(fy[n:n + 1]), force_rowcol=(fr, fc))
+    print("%s: (row, col) tie-breaks %d / %d" % (case_name, n_rc, row.size))
+
+    # ---- MS-SSIM of the final reconstruction, both call forms, per image; and the images themselves
+    worst_ms, worst_px = 0.0, 0.0
+    for n in range(B):
+        xi = np.transpose(x[n], (1, 2, 0)).astype(np.uint8)
+        gi = np.transpose(np.clip(x_with_si[n], 0, 255), (1, 2, 0))
+        a = (float(M.msssim_standard(xi, gi)), float(M.msssim_reference_call(xi, gi)))
+        if n in replay:
+            ri = np.transpose(np.clip(replay[n].x_with_si[0].numpy(), 0, 255), (1, 2, 0))
+            b = (float(M.msssim_standard(xi, ri)), float(M.msssim_reference_call(xi, ri)))
+            ref_img = replay[n].x_with_si[0].numpy()
+        else:
+            b = ref_ms[n]
+            k = list(d["keep"]).index(n) if n in list(d["keep"]) else None
+            ref_img = d["ref_x_with_si"][k] if k is not None else None
+        worst_ms = max(worst_ms, abs(a[0] - b[0]), abs(a[1] - b[1]))
+        if ref_img is not None:
+            worst_px = max(worst_px, float(np.abs(x_with_si[n] - ref_img).max()))
+    print("%s: max |d MS-SSIM| %.2e, max |d x_with_si| %.3f grey levels" % (case_name, worst_ms, worst_px))
+    assert worst_ms <= 1e-4
+    assert worst_px < 2.0  # fp16-operand decoders / SI-Net: dense sub-grey-level noise, no discrete differences left
+
+
+def test_free_running_full_size_batch1():
+    _run("full1")
+
+
+def test_free_running_full_size_batch8_configs1():
+    """BASELINE configs[1]: batch 8 of 320x1224 pairs through AE.siNet_get_reconstructed."""
+    _run("full8")

@@ -10,7 +10,7 @@ import torch
 
 from dsin_b200 import synth
 from oracle import dsin_oracle as O
-from oracle import ms_ssim_oracle as M
+from oracle import ms_ssim_oracle as M  # noqa: F401
 
 from parity_utils import calibrated_weights, make_ae, symbol_report
 
@@ -257,23 +257,17 @@ def test_stagewise_small():
     _stagewise(80, 144, 2, 300)
 
 
-def test_stagewise_and_free_running_full_size():
-    """BASELINE config 1/2 geometry (320x1224).  Stage-wise parity, then the free-running public
-    call: |d bpp| and |d MS-SSIM| against the oracle within the north_star tolerances."""
+def test_stagewise_full_size():
+    """BASELINE config 1/2 geometry (320x1224), every stage fed the oracle's input for that stage.  The free-running
+    public call is held to the north_star tolerances in tests/test_gpu_freerun.py."""
     ae, x, y, ref, rep = _stagewise(320, 1224, 1, 1000)
-    y_dec, y_syn, x_dec, x_with_si, bpp = ae.siNet_get_reconstructed(x, y)
-    n_mism = rep["symbol_mismatch"][0]
-    xi = np.transpose(x[0], (1, 2, 0)).astype(np.uint8)
-    a = float(M.msssim_standard(xi, np.transpose(np.clip(x_with_si[0], 0, 255), (1, 2, 0))))
-    b = float(M.msssim_standard(xi, np.transpose(np.clip(ref.x_with_si[0].numpy(), 0, 255), (1, 2, 0))))
-    a2 = float(M.msssim_reference_call(xi, np.transpose(np.clip(x_with_si[0], 0, 255), (1, 2, 0))))
-    b2 = float(M.msssim_reference_call(xi, np.transpose(np.clip(ref.x_with_si[0].numpy(), 0, 255), (1, 2, 0))))
-    row, col = ae.last["row"].cpu(), ae.last["col"].cpu()
-    agree = float(((row == ref.row) & (col == ref.col)).float().mean())
-    print("full-size report:", rep, "free-running bpp %.7f vs %.7f, msssim %.6f vs %.6f (utils form %.6f vs %.6f), "
-          "rowcol agree %.4f" % (float(bpp), float(ref.bpp), a, b, a2, b2, agree))
-    assert abs(float(bpp) - float(ref.bpp)) <= 1e-5 * (1 + 4 * n_mism)
-    assert abs(a - b) <= 1e-4 * (1 + 4 * n_mism) and abs(a2 - b2) <= 1e-4 * (1 + 4 * n_mism)
+    print("full-size stage-wise report:", rep)
+    # the shipped policy runs the decoders on fp16 operands (precision.py): dense sub-grey-level noise, no outliers
+    enc_ref = O.encode(torch.tensor(x), calibrated_weights(0))
+    x_dec1 = ae.ae_imgcomp.decode(enc_ref.qbar.cuda().contiguous(), terms=1).cpu()
+    diff = (x_dec1 - ref.x_dec).abs()
+    print("fp16-operand decoder vs oracle: max %.3f rms %.4f grey levels" % (float(diff.max()), float(diff.pow(2).mean().sqrt())))
+    assert float(diff.max()) < 1.5 and float(diff.pow(2).mean().sqrt()) < 0.15
 
 
 # ----------------------------------------------------------------------------- tcgen05 trunk conv
@@ -611,3 +605,34 @@ def test_cuda_graph_replay_equals_eager_and_follows_weight_reload():
     ref = ae.siNet_get_reconstructed(x, y)
     for a, b in zip(ref, new):
         assert np.array_equal(np.array(a), b)
+
+
+# ----------------------------------------------------------------------------- kernels vs the reference's own functions
+def test_kernels_match_reference_elementwise_functions(golden_dir):
+    """The CUDA kernels against outputs of the reference's OWN Python (tests/golden/tf_pieces_golden.npz, produced by
+    running the ast-extracted functions under a numpy stand-in for their elementwise tf ops): SI-Finder normalisation +
+    colour transform (src/siFinder.py:56-73,138-154), heatmap and masked bottleneck
+    (src/autoencoder_imgcomp.py:173-201), quantiser (src/quantizer_imgcomp.py:43-100)."""
+    from dsin_b200 import ops
+    g = np.load(os.path.join(golden_dir, "tf_pieces_golden.npz"))
+    # K5: five 20x24 patches side by side form a 20x120 image; q = transformed patches, r = transformed image
+    patches = g["sif_in"]                                              # (5,20,24,3)
+    img = np.ascontiguousarray(np.concatenate(list(patches), axis=1))[None]  # (1,20,120,3)
+    q, r, _ps, _ys = ops.sif_prepare(_dev(img), _dev(img), 20, 24)
+    assert torch.equal(q.cpu().reshape(5, 20, 24, 3), torch.tensor(g["sif_rgb"]))
+    assert torch.equal(r.cpu()[0], torch.tensor(np.concatenate(list(g["sif_rgb"]), axis=1)))
+    # K3 heatmap + mask
+    z33 = g["z33"]
+    c = g["q_centers"]
+    out = ops.heatmap_quantize(_nhwc(_dev(z33)), _dev(c), full=True)
+    hm, z = out[5].cpu(), out[4].cpu()
+    assert float((hm - torch.tensor(g["heatmap3d"])).abs().max()) <= 4e-6
+    assert float((z - torch.tensor(g["z_masked"])).abs().max()) <= 2e-5
+    # K3 quantiser on the golden input: heatmap channel +30 -> H3D == 1 everywhere, so z == q_in exactly
+    z33q = np.concatenate([np.full((2, 1, 6, 7), 30.0, np.float32), g["q_in"]], axis=1)
+    _qn, qbar, sym, qhard, zz, hm1 = ops.heatmap_quantize(_nhwc(_dev(z33q)), _dev(c), full=True)
+    assert torch.equal(hm1.cpu(), torch.ones(2, 32, 6, 7)) and torch.equal(zz.cpu(), torch.tensor(g["q_in"]))
+    assert torch.equal(sym.cpu(), torch.tensor(g["q_symbols"]))        # incl. on-centre and midway inputs
+    assert torch.equal(qhard.cpu(), torch.tensor(g["q_hard"]))
+    qsoft_ref, qhard_ref = torch.tensor(g["q_soft"]), torch.tensor(g["q_hard"])
+    assert float((qbar.cpu() - (qsoft_ref + (qhard_ref - qsoft_ref))).abs().max()) <= 6e-7

@@ -204,3 +204,26 @@ def test_host_helpers_match_reference(golden_dir, tmp_path):
     assert np.array_equal(np.asarray(Image.open(tmp_path / "model" / str(g["png_name"][0]))), g["png_pixels"])
     diff, l1 = utils.l1_x_vs_rec(g["l1_a"], g["l1_b"])
     assert np.array_equal(diff, g["l1_diff"]) and np.float32(l1) == g["l1_value"]
+
+
+# ----------------------------------------------------------------------------- reference code under a numpy tf stand-in
+def test_oracle_matches_reference_elementwise_functions(golden_dir):
+    """tests/golden/tf_pieces_golden.npz holds outputs of the reference's OWN functions (ast-extracted, executed under a
+    numpy stand-in for the elementwise / shape tf ops they call; tests/golden/make_golden.py): SI-Finder normalisation and
+    colour transform (src/siFinder.py:56-73,138-154), heatmap (src/autoencoder_imgcomp.py:173-201), quantiser
+    (src/quantizer_imgcomp.py:43-100), bpp (src/bits_imgcomp.py:4-20).  The oracle must reproduce them."""
+    g = np.load(os.path.join(golden_dir, "tf_pieces_golden.npz"))
+    img = torch.tensor(g["sif_in"])
+    norm = O.sif_normalize_nhwc(img)
+    assert torch.equal(norm, torch.tensor(g["sif_norm"]))
+    assert torch.equal(O.rgb_transform(norm), torch.tensor(g["sif_rgb"]))
+    z33 = torch.tensor(g["z33"])
+    hm = O.heatmap3d(z33)
+    assert float((hm - torch.tensor(g["heatmap3d"])).abs().max()) <= 4e-6  # sigmoid: torch vs 1/(1+exp(-x)) in fp32
+    assert float((hm * z33[:, 1:] - torch.tensor(g["z_masked"])).abs().max()) <= 2e-5
+    qbar, qsoft, qhard, sym = O.quantize(torch.tensor(g["q_in"]), g["q_centers"])
+    assert torch.equal(sym, torch.tensor(g["q_symbols"]))   # incl. the exactly-on-a-centre and the midway cases
+    assert torch.equal(qhard, torch.tensor(g["q_hard"]))
+    assert float((qsoft - torch.tensor(g["q_soft"])).abs().max()) <= 5e-7
+    n_pix = int(np.prod(g["bc_input_shape"])) // 3
+    assert float(O.bitcost_to_bpp(torch.tensor(g["bc"]), n_pix)) == pytest.approx(float(g["bpp"]), rel=2e-7)

@@ -27,6 +27,13 @@ from oracle import ms_ssim_oracle as M  # noqa: E402
 
 
 def enc_stats(z_gpu, sym_gpu, d, tag):
+    if "z64_" + tag not in d:  # light case: symbols and margins only
+        m64 = torch.as_tensor(d["margin64_" + tag])
+        s32 = torch.as_tensor(d["sym32_" + tag]).long()
+        mm32 = sym_gpu.cpu() != s32
+        return {"symbols": int(s32.numel()), "mismatch_vs_fp32": int(mm32.sum()),
+                "max_margin64_of_mismatch": float(m64[mm32].max()) if int(mm32.sum()) else 0.0,
+                "margins64_of_mismatches_vs_fp32": sorted(float(v) for v in m64[mm32].tolist())[-12:]}
     z64 = torch.as_tensor(d["z64_" + tag])
     z32 = torch.as_tensor(d["z32_" + tag]).double()
     zg = z_gpu.cpu().double()
@@ -121,8 +128,8 @@ def main():
             ey = ae.ae_imgcomp.encode(yg, terms=pol.enc_y)
             r["enc_y"] = enc_stats(ey.z, ey.symbols, d, "y")
             # decoder alone, fed the oracle's qbar
-            xd = ae.ae_imgcomp.decode(torch.tensor(d["qbar32_x"]).cuda().contiguous(), terms=pol.dec).cpu().numpy()
-            if len(d["keep"]) == c["B"]:
+            if "qbar32_x" in d and len(d["keep"]) == c["B"]:
+                xd = ae.ae_imgcomp.decode(torch.tensor(d["qbar32_x"]).cuda().contiguous(), terms=pol.dec).cpu().numpy()
                 diff = np.abs(xd - d["ref_x_dec"])
                 r["dec_alone_max"], r["dec_alone_rms"] = float(diff.max()), float(np.sqrt((diff.astype(np.float64) ** 2).mean()))
             r["full"] = full_stats(ae, d, c["B"])
