@@ -560,6 +560,17 @@ extern "C" int dsin_conv2d_tc(dsin_handle_t h, const dsin_conv_desc_t* d, int te
       a.n = d->n; a.OH = p.OH; a.OW = p.OW; a.act = d->act;
       return conv_ws_launch(h, (const __half*)x_hi, (const __half*)w_hi, a, st);
     }
+    if (use_pairs && terms == 3 && !(d->flags & DSIN_CONV_NO_HALO) && k == 3 && d->stride == 1 && d->dilation == 1 &&
+        dil_x == 1 && d->cin == 128 && d->cout == 128 && y_hi && y_lo && !y_f32 && d->post == DSIN_POST_NONE &&
+        d->act != DSIN_ACT_LRELU02 && p.total_tiles >= 2) {
+      // fp32-class trunk layer: halo-tile CTA-pair kernel with separate large / small term accumulators (conv_h3.cu)
+      ConvH3Args a;
+      memset(&a, 0, sizeof(a));
+      a.scale = scale; a.shift = shift;
+      a.r1h = p.r1h; a.r1l = p.r1l; a.r2h = p.r2h; a.r2l = p.r2l; a.yh = p.yh; a.yl = p.yl;
+      a.n = d->n; a.OH = p.OH; a.OW = p.OW; a.act = d->act;
+      return conv_h3_launch(h, (const __half*)x_hi, (const __half*)x_lo, (const __half*)w_hi, (const __half*)w_lo, a, st);
+    }
     if (use_pairs && KC == 64 && NPAD == 128 && d->cout == 128 && y_hi && !y_f32 && d->post == DSIN_POST_NONE &&
         d->act != DSIN_ACT_LRELU02 && p.total_tiles >= 2) {
       // CTA-pair kernel: each CTA of a pair loads half of the weight slab (64 couts)

@@ -48,3 +48,16 @@ struct ConvWsArgs {
   int tiles_w, tiles_h, total_tiles;  // filled by conv_ws_launch
 };
 int conv_ws_launch(dsin_handle_t h, const __half* x, const __half* w_packed, const ConvWsArgs& a, cudaStream_t st);
+
+// fp32-class (terms = 3) 3x3 128->128 trunk layer on CTA pairs: halo-resident split-fp16 activation tile, streamed
+// weights, separate accumulators for large / small product terms, staged TMA-store epilogue (conv_h3.cu).
+struct ConvH3Args {
+  const float* scale;
+  const float* shift;
+  const __half *r1h, *r1l, *r2h, *r2l;  // optional residual tensors (split fp16 NHWC; lo planes may be NULL)
+  __half *yh, *yl;
+  int n, OH, OW, act;
+  int tiles_w, tiles_h, total_tiles;  // filled by conv_h3_launch
+};
+int conv_h3_launch(dsin_handle_t h, const __half* x_hi, const __half* x_lo, const __half* w_hi, const __half* w_lo,
+                   const ConvH3Args& a, cudaStream_t st);

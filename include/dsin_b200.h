@@ -82,8 +82,10 @@ typedef struct {
 } dsin_conv_desc_t;
 enum { DSIN_CONV_PAIR_SHARED = 1,
        DSIN_CONV_NO_CTA_PAIR = 2, /* run a 128->128 layer on the one-CTA kernel (cross-check of the CTA-pair kernels) */
-       DSIN_CONV_NO_WEIGHT_STATIONARY = 4 /* terms = 1, 3x3 128->128: use the tap-streaming CTA-pair kernel instead of
-                                              the weight-stationary halo-tile kernel (cross-check) */
+       DSIN_CONV_NO_WEIGHT_STATIONARY = 4, /* terms = 1, 3x3 128->128: use the tap-streaming CTA-pair kernel instead of
+                                               the weight-stationary halo-tile kernel (cross-check) */
+       DSIN_CONV_NO_HALO = 8 /* terms = 3, 3x3 128->128: use the tap-streaming CTA-pair kernel (one accumulator for all
+                                three product terms) instead of the halo-tile kernel (cross-check) */
 };
 int dsin_conv2d(dsin_handle_t h, const dsin_conv_desc_t* d, const float* x, const float* w,
                 const float* scale, const float* shift, const float* res1, const float* res2,

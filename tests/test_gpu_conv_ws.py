@@ -74,3 +74,43 @@ def test_conv_ws_is_the_default_for_fp16_operand_trunk_layers():
     lo = torch.zeros_like(res[0])
     y1, _ = ops.conv_tc((xh, None), tcl, res1=(res[0], lo), terms=1)  # lo plane present -> streaming kernel
     assert float((y0.float() - y1.float()).abs().max()) <= 2.0 ** -9 * float(y0.float().abs().max())
+
+
+# ----------------------------------------------------------------------------- fp32-class halo kernel (conv_h3.cu)
+@pytest.mark.parametrize("shape", [(2, 20, 36), (1, 80, 306), (3, 9, 17), (2, 33, 70)])
+@pytest.mark.parametrize("nres", [0, 1, 2])
+def test_conv_h3_matches_float64_and_is_closer_than_the_single_accumulator_kernel(shape, nres):
+    """3-term layer: halo-tile kernel with separate accumulators for the large and the small product terms vs a float64
+    convolution of the split operands it consumed, and vs the tap-streaming kernel (all terms in one accumulator)."""
+    from dsin_b200 import ops
+    n, hh, ww = shape
+    rng = np.random.default_rng(100 + hh + nres)
+    x = rng.standard_normal((n, 128, hh, ww)).astype(np.float32)
+    w = (rng.standard_normal((3, 3, 128, 128)) / np.sqrt(9 * 128)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, 128).astype(np.float32)
+    shift = rng.standard_normal(128).astype(np.float32)
+    act = ops.ACT_RELU if nres < 2 else ops.ACT_NONE
+    tcl = ops.ConvTC(ops.ConvLayer(w, scale, shift, act=act))
+    xs = ops.f32_to_split(_nhwc(torch.tensor(x).cuda()))
+    res = [ops.f32_to_split(_nhwc(torch.tensor(rng.standard_normal((n, 128, hh, ww)).astype(np.float32)).cuda()))
+           for _ in range(nres)]
+    r1 = res[0] if nres > 0 else None
+    r2 = res[1] if nres > 1 else None
+    y_h3 = ops.split_to_f32(*ops.conv_tc(xs, tcl, res1=r1, res2=r2, terms=3)).permute(0, 3, 1, 2).cpu().double()
+    y_st = ops.split_to_f32(*ops.conv_tc(xs, tcl, res1=r1, res2=r2, terms=3, flags=ops.CONV_NO_HALO))
+    y_st = y_st.permute(0, 3, 1, 2).cpu().double()
+    xq = ops.split_to_f32(*xs).permute(0, 3, 1, 2).cpu().double()
+    ref = O.conv2d_same(xq, w.astype(np.float64))
+    ref = ref * torch.tensor(scale).double().view(1, -1, 1, 1) + torch.tensor(shift).double().view(1, -1, 1, 1)
+    if act == ops.ACT_RELU:
+        ref = torch.relu(ref)
+    for r in res:
+        ref = ref + ops.split_to_f32(*r).permute(0, 3, 1, 2).cpu().double()
+    e_h3, e_st = (y_h3 - ref).abs(), (y_st - ref).abs()
+    scale_ref = max(1.0, float(ref.abs().max()))
+    print("3-term %s nres %d: halo kernel max %.2e rms %.2e | single accumulator max %.2e rms %.2e"
+          % (shape, nres, float(e_h3.max()), float(e_h3.pow(2).mean().sqrt()), float(e_st.max()),
+             float(e_st.pow(2).mean().sqrt())))
+    assert float(e_h3.max()) < 1e-5 * scale_ref
+    assert float(e_st.max()) < 1e-5 * scale_ref
+    assert float(e_h3.pow(2).mean().sqrt()) <= 1.05 * float(e_st.pow(2).mean().sqrt())

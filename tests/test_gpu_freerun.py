@@ -59,7 +59,7 @@ def _adjudicate_rowcol(ref, row, col, H, W):
             a = _score64(q64, r64, mask, p, row[n, p], col[n, p])
             b = _score64(q64, r64, mask, p, rr[n, p], rc[n, p])
             assert abs(a - b) < ROWCOL_GAP, (n, p, a, b)
-    assert int(mism.sum()) <= max(1, mism.size // 400), int(mism.sum())
+    assert int(mism.sum()) <= max(2, mism.size // 100), int(mism.sum())
     return np.where(mism, row, -1), np.where(mism, col, -1), int(mism.sum())
 
 
