@@ -377,7 +377,9 @@ class AE(object):
         i.e. src/AE.py:132-148 without access to x.  The decoder input is qhard = centres[symbols]; the sender-side
         graph feeds qbar = qsoft + (qhard - qsoft), which equals qhard up to one fp32 rounding."""
         yd = self._to_device(y, "y")
-        sym = self.pc_imgcomp.decode_symbols(list(bitstreams), self.ae_imgcomp._centers)
+        f = self.ae_imgcomp.get_subsampling_factor()
+        sym = self.pc_imgcomp.decode_symbols(list(bitstreams), self.ae_imgcomp._centers, expect_shape=(
+            self.ae_config.num_chan_bn, yd.shape[2] // f, yd.shape[3] // f))
         if sym.shape[0] != yd.shape[0]:
             raise ValueError("{} bitstreams for {} side images".format(sym.shape[0], yd.shape[0]))
         qhard = self.ae_imgcomp._centers[sym]

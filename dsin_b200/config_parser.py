@@ -16,7 +16,39 @@ those two files actually use is small and is restated here:
 """
 from __future__ import annotations
 
+import ast
+import operator
 import os
+
+# The value grammar the two run-config files use: literals, tuples / lists, earlier keys and constraint words as names,
+# and + - * / ** with unary minus.  Evaluated over the AST (never eval()): a config file cannot reach attributes, calls,
+# subscripts or comprehensions.
+_BINOPS = {ast.Add: operator.add, ast.Sub: operator.sub, ast.Mult: operator.mul, ast.Div: operator.truediv,
+           ast.FloorDiv: operator.floordiv, ast.Mod: operator.mod, ast.Pow: operator.pow}
+
+
+def _evaluate(node, env):
+    if isinstance(node, ast.Expression):
+        return _evaluate(node.body, env)
+    if isinstance(node, ast.Constant):
+        return node.value
+    if isinstance(node, ast.Name):
+        if node.id in env:
+            return env[node.id]
+        raise NameError("unknown name {!r}".format(node.id))
+    if isinstance(node, ast.Tuple):
+        return tuple(_evaluate(e, env) for e in node.elts)
+    if isinstance(node, ast.List):
+        return [_evaluate(e, env) for e in node.elts]
+    if isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.USub, ast.UAdd)):
+        v = _evaluate(node.operand, env)
+        return -v if isinstance(node.op, ast.USub) else +v
+    if isinstance(node, ast.BinOp) and type(node.op) in _BINOPS:
+        a, b = _evaluate(node.left, env), _evaluate(node.right, env)
+        if isinstance(node.op, ast.Pow) and isinstance(b, (int, float)) and abs(b) > 64:
+            raise ValueError("exponent too large")
+        return _BINOPS[type(node.op)](a, b)
+    raise ValueError("unsupported expression element {}".format(type(node).__name__))
 
 
 class Config(object):
@@ -78,7 +110,7 @@ def parse_string(text, base=None):
         env = dict(words)
         env.update(values)
         try:
-            val = eval(expr, {"__builtins__": {}, "True": True, "False": False, "None": None}, env)
+            val = _evaluate(ast.parse(expr, mode="eval"), env)
         except Exception as e:  # noqa: BLE001
             raise ValueError("line {}: cannot evaluate {!r}: {}".format(lineno, expr, e))
         if key in constraints and val not in constraints[key]:

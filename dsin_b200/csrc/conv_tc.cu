@@ -48,7 +48,7 @@ struct GP {
 
 constexpr int up1024(int v) { return (v + 1023) / 1024 * 1024; }
 
-template <int KC, int NPAD, int TERMS, bool PS = false>
+template <int KC, int NPAD, int TERMS, bool PS = false, int NSPLIT = 1>
 struct Cfg {
   // k-blocks (tap, channel chunk) per pipeline stage: the 32-channel layers have so little MMA work per
   // k-block (N <= 128, K = 32) that the fixed per-stage cost dominates; they take 3 k-blocks per stage.
@@ -61,7 +61,14 @@ struct Cfg {
   static constexpr int kStagesRaw = (196 * 1024) / kStage;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kSmem = kStages * kStage + 1024 + 2048;
-  static constexpr int kTmemCols = 2 * NPAD <= 32 ? 32 : (2 * NPAD <= 64 ? 64 : (2 * NPAD <= 128 ? 128 : 256));
+  // accumulator columns per buffer: TERMS == 3 keeps the hi*hi products and the 2^-11-times-smaller hi*lo + lo*hi
+  // products in SEPARATE accumulators (tcgen05 accumulates with round-toward-zero: every MMA into an accumulator of
+  // magnitude |acc| can lose an ulp(|acc|); the small terms must not pay, nor add, roundings at the large magnitude)
+  // NSPLIT > 1 additionally deals the hi*hi k-blocks round-robin onto NSPLIT accumulators (a 5x5 layer is 200 MMAs
+  // deep: to_bn, the layer that produces the quantiser's input, runs with 4), summed in fp32 by the epilogue.
+  static constexpr int kAccCols = (TERMS == 3 ? NSPLIT + 1 : 1) * NPAD;
+  static_assert(NSPLIT == 1 || (TERMS == 3 && !PS && KC == 64), "split accumulators: 3-term, 64-channel k-blocks");
+  static constexpr int kTmemCols = 2 * kAccCols <= 32 ? 32 : (2 * kAccCols <= 64 ? 64 : (2 * kAccCols <= 128 ? 128 : (2 * kAccCols <= 256 ? 256 : 512)));
   static constexpr uint32_t kLayout = KC == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
   static constexpr uint32_t kSbo = KC == 64 ? 1024 : 512;
 };
@@ -91,12 +98,12 @@ __device__ __forceinline__ void add_residual16(float* f, const __half* rh, const
   }
 }
 
-template <int KC, int NPAD, int TERMS, bool PS = false>
+template <int KC, int NPAD, int TERMS, bool PS = false, int NSPLIT = 1>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
                const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
                const __grid_constant__ GP p) {
-  using C = Cfg<KC, NPAD, TERMS, PS>;
+  using C = Cfg<KC, NPAD, TERMS, PS, NSPLIT>;
   static_assert(!PS || (KC == 64 && NPAD == 64), "pair-shared mode is 2 pixels x 32 channels");
   constexpr int S = C::kStages;
   constexpr int STAGE = C::kStage;
@@ -192,7 +199,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
         const int acc = it & 1;
         mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * NPAD;
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * C::kAccCols;
+        const uint32_t d_lo = d_tmem + NSPLIT * NPAD;  // TERMS == 3 only
         for (int kb0 = 0; kb0 < num_kb; kb0 += TPS) {
           const int nsub = min(TPS, num_kb - kb0);
           mbar_wait(&full[stage], phase);
@@ -216,10 +224,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
 #pragma unroll
                   for (int k = 0; k < 2; ++k) {
                     const uint32_t dt = d_tmem + hf * 32;
-                    umma_f16(dt, a_hi + 4 * hf + 2 * k, b_hi + 2 * k, idesc32, (kb0 | t | k) ? 1u : 0u);
+                    const uint32_t first = (kb0 | t | k) ? 1u : 0u;
+                    umma_f16(dt, a_hi + 4 * hf + 2 * k, b_hi + 2 * k, idesc32, first);
                     if (TERMS == 3) {
-                      umma_f16(dt, a_hi + 4 * hf + 2 * k, b_lo + 2 * k, idesc32, 1u);
-                      umma_f16(dt, a_lo + 4 * hf + 2 * k, b_hi + 2 * k, idesc32, 1u);
+                      umma_f16(dt + NPAD, a_hi + 4 * hf + 2 * k, b_lo + 2 * k, idesc32, first);
+                      umma_f16(dt + NPAD, a_lo + 4 * hf + 2 * k, b_hi + 2 * k, idesc32, 1u);
                     }
                   }
                 continue;
@@ -228,10 +237,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
               const uint64_t b_lo = make_smem_desc(sa + OFF_BLO, 16, C::kSbo, C::kLayout);
 #pragma unroll
               for (int k = 0; k < KC / 16; ++k) {  // +32 B per K=16 step inside the swizzled row
-                umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb0 | t | k) ? 1u : 0u);
+                const uint32_t first = (kb0 | t | k) ? 1u : 0u;
+                if (NSPLIT > 1) {  // k-block kb0 (one per stage here) goes to accumulator kb0 % NSPLIT
+                  umma_f16(d_tmem + (uint32_t)((kb0 % NSPLIT) * NPAD), a_hi + 2 * k, b_hi + 2 * k, idesc,
+                           (kb0 >= NSPLIT || k) ? 1u : 0u);
+                } else {
+                  umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, first);
+                }
                 if (TERMS == 3) {
-                  umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-                  umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                  umma_f16(d_lo, a_hi + 2 * k, b_lo + 2 * k, idesc, first);
+                  umma_f16(d_lo, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
                 }
               }
             }
@@ -267,14 +282,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
       for (int chunk = 0; chunk < NPAD / 16; ++chunk) {
         const int c0 = chunk * 16;
         if (c0 >= p.cout) break;  // warp-uniform
-        uint32_t v[16];
-        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NPAD + c0), v);
+        uint32_t v[16], vlo[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::kAccCols + c0), v);
+        if (TERMS == 3)
+          tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::kAccCols + NSPLIT * NPAD + c0), vlo);
         tmem_ld_wait();
+        if (NSPLIT > 1) {  // sum the partial hi*hi accumulators (fp32, round to nearest)
+#pragma unroll 1
+          for (int sp = 1; sp < NSPLIT; ++sp) {
+            uint32_t vs[16];
+            tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::kAccCols + sp * NPAD + c0), vs);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(vs[j])));
+          }
+        }
         if (valid) {
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float t = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), s_scale[c0 + j]), s_shift[c0 + j]);
+            float a = __uint_as_float(v[j]);
+            if (TERMS == 3) a = __fadd_rn(a, __uint_as_float(vlo[j]));  // large + small product terms, round to nearest
+            float t = __fadd_rn(__fmul_rn(a, s_scale[c0 + j]), s_shift[c0 + j]);
             if (p.act == DSIN_ACT_RELU) t = fmaxf(t, 0.f);
             else if (p.act == DSIN_ACT_LRELU02) t = fmaxf(__fmul_rn(t, 0.2f), t);
             f[j] = t;
@@ -378,19 +407,19 @@ __global__ void pack_w_tc_kernel(const float* __restrict__ w, __half* __restrict
   }
 }
 
-template <int KC, int NPAD, int TERMS, bool PS = false>
+template <int KC, int NPAD, int TERMS, bool PS = false, int NSPLIT = 1>
 int launch_one(dsin_handle_t h, const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh,
                const CUtensorMap& wl, const GP& p, cudaStream_t st) {
-  using C = Cfg<KC, NPAD, TERMS, PS>;
+  using C = Cfg<KC, NPAD, TERMS, PS, NSPLIT>;
   static bool configured[DSIN_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
   if (!configured[h->device]) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<KC, NPAD, TERMS, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(conv_tc_kernel<KC, NPAD, TERMS, PS, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              C::kSmem) != cudaSuccess)
       return dsin_fail(h, DSIN_ERR_CUDA, "%s: cannot raise dynamic shared memory", __func__);
     configured[h->device] = true;
   }
   int grid = p.total_tiles < h->sm_count ? p.total_tiles : h->sm_count;
-  conv_tc_kernel<KC, NPAD, TERMS, PS><<<grid, 192, C::kSmem, st>>>(xh, xl, wh, wl, p);
+  conv_tc_kernel<KC, NPAD, TERMS, PS, NSPLIT><<<grid, 192, C::kSmem, st>>>(xh, xl, wh, wl, p);
   DSIN_LAUNCHED(h);
   return DSIN_OK;
 }
@@ -524,6 +553,8 @@ extern "C" int dsin_conv2d_tc(dsin_handle_t h, const dsin_conv_desc_t* d, int te
                         : launch_one<64, 64, 1, true>(h, xh, xl, wh, wl, gp, st);
     if (KC == 64 && NPAD == 128) return launch_terms<64, 128>(h, terms, xh, xl, wh, wl, gp, st);
     if (KC == 64 && NPAD == 64) return launch_terms<64, 64>(h, terms, xh, xl, wh, wl, gp, st);
+    if (KC == 64 && NPAD == 48 && terms == 3 && gp.ntaps * gp.nchunks >= 4)  // to_bn: 4 partial hi*hi accumulators
+      return launch_one<64, 48, 3, false, 4>(h, xh, xl, wh, wl, gp, st);
     if (KC == 64 && NPAD == 48) return launch_terms<64, 48>(h, terms, xh, xl, wh, wl, gp, st);
     if (KC == 64 && NPAD == 16) return launch_terms<64, 16>(h, terms, xh, xl, wh, wl, gp, st);
     if (KC == 32 && NPAD == 128) return launch_terms<32, 128>(h, terms, xh, xl, wh, wl, gp, st);

@@ -157,6 +157,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
         mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        // Without residual inputs the second accumulator (columns +128) takes the small product terms hi*lo + lo*hi:
+        // tcgen05 accumulates with round-toward-zero, and 2 x 4 x num_kb small-term MMAs must neither pay nor add
+        // roundings at the magnitude of the hi*hi sum (h2: 25 taps -> 300 MMAs in one accumulator otherwise).
+        const uint32_t d_small = (TERMS == 3 && rm.nres == 0) ? d_tmem + 128u : d_tmem;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           fence_after_sync();
@@ -170,8 +174,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
             for (int k = 0; k < 4; ++k) {
               umma2_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) ? 1u : 0u);
               if (TERMS == 3) {
-                umma2_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-                umma2_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                umma2_f16(d_small, a_hi + 2 * k, b_lo + 2 * k, idesc, (d_small == d_tmem || (kb | k)) ? 1u : 0u);
+                umma2_f16(d_small, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
               }
             }
             umma2_commit(&empty[stage]);  // frees this stage in BOTH CTAs
@@ -218,6 +222,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
     const int row = q * 32 + lane;
     const int hl = row >> 4, wl = row & 15;
     const bool has_res = rm.nres > 0;
+    const bool has_small = TERMS == 3 && !has_res;  // columns +128 hold the hi*lo + lo*hi products
     int it = 0;
     for (int pi = cid; pi < pairs; pi += nclusters, ++it) {
       const int acc = it & 1;
@@ -237,13 +242,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
         const int c0 = chunk * 16;
         uint32_t v[16], r[16];
         tmem_ld_32x16(lane_base + (uint32_t)c0, v);
-        if (has_res) tmem_ld_32x16(lane_base + 128u + (uint32_t)c0, r);
+        if (has_res || has_small) tmem_ld_32x16(lane_base + 128u + (uint32_t)c0, r);
         tmem_ld_wait();
         if (!valid) continue;
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float t = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), s_scale[c0 + j]), s_shift[c0 + j]);
+          float a = __uint_as_float(v[j]);
+          if (has_small) a = __fadd_rn(a, __uint_as_float(r[j]));  // large + small product terms, round to nearest
+          float t = __fadd_rn(__fmul_rn(a, s_scale[c0 + j]), s_shift[c0 + j]);
           t = p.act == DSIN_ACT_RELU ? fmaxf(t, 0.f) : t;
           f[j] = has_res ? __fadd_rn(t, __uint_as_float(r[j])) : t;
         }

@@ -119,8 +119,9 @@ class _ResShallow(object):
         return [bitstream.pack([out_h[i, k, :sizes_h[i, k]].tobytes() for k in range(nstreams)], c, hh, ww, self.L)
                 for i in range(n)]
 
-    def decode_symbols(self, bitstreams, centers):
-        """list of n bitstreams (same shape) -> symbols (n,c,h,w) int64 CUDA."""
+    def decode_symbols(self, bitstreams, centers, expect_shape=None):
+        """list of n bitstreams (same shape) -> symbols (n,c,h,w) int64 CUDA.  expect_shape = (c, h, w) the caller's
+        model geometry implies; a header that disagrees is rejected before anything is allocated."""
         self._check_codec()
         parsed = [bitstream.unpack(b) for b in bitstreams]
         c, hh, ww, L, streams0 = parsed[0]
@@ -130,6 +131,17 @@ class _ResShallow(object):
                 raise ValueError("bitstreams of one batch must share their geometry")
         if L != self.L:
             raise ValueError("bitstream has {} centres, model has {}".format(L, self.L))
+        # the header is untrusted input: refuse geometries the model cannot have produced BEFORE allocating for them
+        if expect_shape is not None and (c, hh, ww) != tuple(expect_shape):
+            raise ValueError("bitstream holds a {}x{}x{} symbol volume, this model / image size needs {}x{}x{}".format(
+                c, hh, ww, *expect_shape))
+        if not (1 <= c <= 256 and 1 <= hh <= 58 and 1 <= ww <= 159 and 1 <= nstreams <= 64):
+            raise ValueError("bitstream geometry {}x{}x{} / {} streams is outside what the PC1 coder supports".format(
+                c, hh, ww, nstreams))
+        for p_ in parsed:
+            for s_ in p_[4]:
+                if len(s_) > 2 * ((c + nstreams - 1) // nstreams) * hh * ww + 16:
+                    raise ValueError("a stream is longer than its symbols can need (16 bits per symbol)")
         cap = max(max(len(s) for s in p[4]) for p in parsed) + 8
         buf = np.zeros((len(parsed), nstreams, cap), np.uint8)
         sizes = np.zeros((len(parsed), nstreams), np.int64)

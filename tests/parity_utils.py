@@ -42,10 +42,11 @@ def make_ae(H, W, weights, precision=None):
               precision=precision)
 
 
-def symbol_report(sym_gpu, x_np, W, margin_tol=1e-3):
+def symbol_report(sym_gpu, x_np, W, margin_tol=1e-4):
     """Compare GPU symbols with the fp32 oracle; every mismatch must be a near-tie according to
-    the float64 oracle (the two nearest centres are within margin_tol of equidistant; z is O(1) and
-    fp32-class arithmetic through 34 conv layers of a random-init net deviates by ~1e-4)."""
+    the float64 oracle: the two nearest centres are within margin_tol of equidistant.  Measured (tools/precision_probe.py):
+    the GPU's z deviates from the float64 oracle by 7.6e-6 rms (the fp32 CPU oracle: 1e-6) and the largest margin of any
+    flipped symbol on nine 320x1224 images was 5e-5."""
     enc32 = O.encode(torch.as_tensor(x_np, dtype=torch.float32), W)
     mism = (sym_gpu != enc32.symbols)
     n_mism = int(mism.sum())

@@ -20,7 +20,7 @@ from parity_utils import make_ae
 
 pytestmark = pytest.mark.gpu
 
-SYMBOL_MARGIN = 6e-4   # float64 |d1 - d2| below which the fp32-class GPU path may pick the other centre
+SYMBOL_MARGIN = 1e-4   # float64 |d1 - d2| below which the fp32-class GPU path may pick the other centre
 ROWCOL_GAP = 5e-4      # float64 score gap below which the argmax may pick the other position: the shipped policy
                        # decodes x_dec / y_dec with fp16 operands (0.07 grey levels rms), which moves a masked Pearson
                        # score by up to ~2e-4; a flip is accepted only between positions at least this close
@@ -35,7 +35,7 @@ def _forced(gpu_sym, ref_sym, margin64, what):
         worst = float(margin64[mism].max())
         print("%s: %d / %d symbols differ from the fp32 oracle; float64 margins up to %.2e" % (what, n, mism.size, worst))
         assert worst < SYMBOL_MARGIN, (what, worst)
-    assert n <= max(2, mism.size // 25000), (what, n)
+    assert n <= max(2, mism.size // 100000), (what, n)
     return np.where(mism, gpu_sym, -1), n
 
 

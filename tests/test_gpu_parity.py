@@ -221,7 +221,7 @@ def _stagewise(H, W, B, seed):
     enc = ae.ae_imgcomp.encode(_dev(x))
     n_mism, bad, total = symbol_report(enc.symbols.cpu(), x, Wt)
     assert bad == 0, "symbol mismatches that are not float64 near-ties: %d" % bad
-    assert n_mism <= max(2, total // 20000), (n_mism, total)
+    assert n_mism <= max(2, total // 100000), (n_mism, total)
     rep["symbol_mismatch"] = (n_mism, total)
     # (b) probability model on the oracle's qbar/symbols
     enc_ref = O.encode(torch.tensor(x), Wt)
@@ -414,7 +414,7 @@ def test_config4_geometry_320x960_encoder_quantizer_probclass():
     x, _ = synth.make_batch(2, 320, 960, seed=4000)
     enc = ae.ae_imgcomp.encode(_dev(x))
     n_mism, bad, total = symbol_report(enc.symbols.cpu(), x, Wt)
-    assert bad == 0 and n_mism <= max(2, total // 20000), (n_mism, bad, total)
+    assert bad == 0 and n_mism <= max(2, total // 100000), (n_mism, bad, total)
     enc_ref = O.encode(torch.tensor(x), Wt)
     ref_bits = O.probclass_bitcost(enc_ref.qbar, enc_ref.symbols, Wt)
     bc = ae.pc_imgcomp.bitcost(enc_ref.qbar.cuda().contiguous(), enc_ref.symbols.cuda(), False,
@@ -636,3 +636,63 @@ def test_kernels_match_reference_elementwise_functions(golden_dir):
     assert torch.equal(qhard.cpu(), torch.tensor(g["q_hard"]))
     qsoft_ref, qhard_ref = torch.tensor(g["q_soft"]), torch.tensor(g["q_hard"])
     assert float((qbar.cpu() - (qsoft_ref + (qhard_ref - qsoft_ref))).abs().max()) <= 6e-7
+
+
+def test_sender_receiver_round_trip_matches_the_one_call_path():
+    """compress(x) -> bytes -> decompress(bytes, y): the receiver feeds the decoder qhard = centres[symbols] while the
+    one-call path (and the reference, src/AE.py:56) feeds qbar = qsoft + (qhard - qsoft), one fp32 rounding away.
+    The gap must stay at rounding level: same symbols, same (row, col), images within 0.05 grey levels."""
+    ae = make_ae(80, 144, calibrated_weights(0))
+    x, y = synth.make_batch(2, 80, 144, seed=55)
+    x8, y8 = x.astype(np.uint8), y.astype(np.uint8)
+    one = [np.array(a) for a in ae.siNet_get_reconstructed(x8, y8)]
+    sym_one = ae.last["symbols"].clone()
+    row_one, col_one = ae.last["row"].clone(), ae.last["col"].clone()
+    blobs = ae.compress(x8)
+    y_dec, y_syn, x_dec, x_with_si = [np.array(a) for a in ae.decompress(blobs, y8)]
+    assert torch.equal(ae.last["symbols"], sym_one)
+    assert torch.equal(ae.last["row"], row_one) and torch.equal(ae.last["col"], col_one)
+    assert np.array_equal(y_dec, one[0]) and np.array_equal(y_syn, one[1])
+    assert float(np.abs(x_dec - one[2]).max()) < 0.05 and float(np.abs(x_with_si - one[3]).max()) < 0.05
+    with pytest.raises(ValueError):  # a container of another geometry is refused from its header
+        make_ae(160, 144, calibrated_weights(0)).decompress(blobs, np.zeros((2, 3, 160, 144), np.uint8))
+
+
+def test_load_model_variable_selection_follows_the_reference(tmp_path):
+    """src/AE.py:158-175: the SI-Net scope is restored when load_train_step, or when testing without training; a
+    first SI training run from an AE-only checkpoint (train_model) restores the AE scopes and keeps the SI-Net's
+    initialiser values."""
+    from dsin_b200 import tf_checkpoint
+    Wt = calibrated_weights(0)
+    ae_only = {k: v for k, v in Wt.items() if not k.startswith("siNetwork/")}
+    prefix = str(tmp_path / "ae_only" / "model")
+    tf_checkpoint.write_checkpoint(prefix, ae_only)
+    ae = make_ae(80, 144, synth.make_weights(5))
+    with pytest.raises(KeyError):          # test_model=True, train_model=False: siNetwork/* is part of the restore list
+        ae.load_model(prefix)
+    ae.ae_config.train_model, ae.ae_config.test_model = True, False
+    si_before = {k: v.copy() for k, v in ae.weights.items() if k.startswith("siNetwork/")}
+    ae.load_model(prefix)
+    for k, v in si_before.items():
+        assert np.array_equal(ae.weights[k], v)                      # SI-Net kept
+    assert np.array_equal(ae.weights[O.ENC + "h1/weights"], Wt[O.ENC + "h1/weights"])  # AE restored
+
+
+def test_sharded_batch_equals_whole_batch_bit_for_bit():
+    """BASELINE configs[4] / SURVEY 8e: the same global batch on 1 and on 2 GPUs gives bit-identical per-image outputs.
+    Needs two GPUs (gpurun --gpus 2); with one GPU the single-process half of the script still checks that batch
+    composition (micro-batch size 3 vs the whole shard) changes nothing."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tests", "multi_gpu_equivalence.py")
+    n = min(2, torch.cuda.device_count())
+    if n >= 2:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+               "127.0.0.1", "--master-port", "29631", script, "--global-batch", "6", "--hw", "160x288"]
+    else:
+        cmd = [sys.executable, script, "--global-batch", "5", "--hw", "160x288"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
+    assert '"identical_per_image": true' in line, line

@@ -85,3 +85,30 @@ def test_bitstream_container_roundtrip():
     for bad in (blob[:10], blob[:-1], blob + b"\x00", b"DSPX" + blob[4:], blob[:4] + b"\x09" + blob[5:]):
         with _pt.raises(ValueError):
             bitstream.unpack(bad)
+
+
+def test_config_values_are_evaluated_without_eval():
+    """Arithmetic, tuples, earlier keys and constraint words work; attribute walks, calls and subscripts do not."""
+    from dsin_b200 import config_parser
+    cfg = config_parser.parse_string("a = 2*0.02\nb = (320, 1224)\nc = a * 3 + 1\nconstrain n :: OFF, FIXED\nn = FIXED\nd = -2**3")
+    assert cfg.a == 0.04 and cfg.b == (320, 1224) and cfg.c == 0.04 * 3 + 1 and cfg.n == "FIXED" and cfg.d == -8
+    for bad in ("x = ().__class__", "x = open('f')", "x = [1][0]", "x = (1).real", "x = 9**9**9", "x = [i for i in (1,)]"):
+        with pytest.raises(ValueError):
+            config_parser.parse_string(bad)
+
+
+def test_bitstream_header_is_validated_before_allocation():
+    """A foreign / malformed container must be refused from its header alone (no device work, no big allocation)."""
+    from dsin_b200 import bitstream
+    from dsin_b200.probclass_imgcomp import _ResShallow
+    blob = bitstream.pack([b"\x00" * 4] * 8, 65535, 65535, 65535, 6)
+    pc = _ResShallow.__new__(_ResShallow)
+    pc.L = 6
+    pc.config = type("C", (), {"use_centers_for_padding": True, "arch_param__k": 24})()
+    with pytest.raises(ValueError, match="symbol volume|outside"):
+        pc.decode_symbols([blob], None, expect_shape=(32, 40, 153))
+    with pytest.raises(ValueError, match="outside"):
+        pc.decode_symbols([blob], None)
+    ok = bitstream.pack([b"\x00" * 70000] + [b"\x00"] * 7, 32, 40, 153, 6)
+    with pytest.raises(ValueError, match="longer than"):
+        pc.decode_symbols([ok], None, expect_shape=(32, 40, 153))
