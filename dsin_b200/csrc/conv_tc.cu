@@ -443,6 +443,26 @@ int conv_tc_valid3d(dsin_handle_t h, const ConvTc3dArgs& a, cudaStream_t st) {
     return dsin_fail(h, DSIN_ERR_UNSUPPORTED, "%s: 3-D tensor-core conv needs cin == 32", __func__);
   const int NPAD = npad_of(a.cout);
   const int Do = a.D - a.kd + 1, Ho = a.H - a.kh + 1, Wo = a.W - a.kw + 1;
+  if (a.kd == 2 && a.kh == 3 && a.kw == 3 && a.ntaps <= 18 && NPAD <= 32) {
+    // halo-tile kernel: one TMA box per tile instead of one per tap, resident filter (conv_h32.cu)
+    ConvH32Args q;
+    memset(&q, 0, sizeof(q));
+    q.scale = a.scale; q.shift = a.shift;
+    q.yh = (__half*)a.y_hi; q.yl = (__half*)a.y_lo; q.yf = a.y_f32;
+    q.r1f = a.r1f; q.r1_d = a.r1_d; q.r1_oh = a.r1_oh; q.r1_ow = a.r1_ow;
+    q.r1_dz = a.r1_dz; q.r1_dy = a.r1_dy; q.r1_dx = a.r1_dx; q.r1_c = a.r1_c ? a.r1_c : a.cout;
+    q.n_out = a.vols * Do; q.dout = Do; q.din = a.D;
+    q.OH = Ho; q.OW = Wo; q.cout = a.cout; q.act = a.act; q.terms = a.terms;
+    q.ntaps = a.ntaps;
+    for (int t = 0; t < a.ntaps; ++t) {
+      q.tz[t] = a.tap_d[t]; q.ty[t] = a.tap_h[t]; q.tx[t] = a.tap_w[t]; q.tw[t] = a.tap_wi[t];
+    }
+    q.hw = 8 + a.kw - 1; q.hh = 16 + a.kh - 1; q.hd = a.kd;
+    q.ox = 0; q.oy = 0;
+    const int rc = conv_h32_launch(h, (const __half*)a.x_hi, (const __half*)a.x_lo, (const __half*)a.w_hi,
+                                   (const __half*)a.w_lo, a.W, a.H, a.vols * a.D, a.wtaps, q, st);
+    if (rc != DSIN_ERR_UNSUPPORTED) return rc;
+  }
   CUtensorMap xh, xl, wh, wl;
   const uint64_t xd[4] = {32, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.vols * a.D};
   const uint64_t xs[3] = {64, (uint64_t)a.W * 64, (uint64_t)a.H * a.W * 64};
@@ -579,6 +599,25 @@ extern "C" int dsin_conv2d_tc(dsin_handle_t h, const dsin_conv_desc_t* d, int te
       }
     p.tiles_w = (p.GW + BW - 1) / BW; p.tiles_h = (p.GH + BH - 1) / BH;
     p.total_tiles = d->n * p.tiles_w * p.tiles_h;
+    if (!(d->flags & (DSIN_CONV_NO_HALO | DSIN_CONV_PAIR_SHARED)) && k == 3 && d->stride == 1 && d->cin == 32 &&
+        d->cout == 32 && d->dilation >= 1 && d->dilation <= 4 && dil_x == d->dilation && y_hi && !y_f32 && !res1_hi &&
+        !res2_hi && d->post == DSIN_POST_NONE && (terms == 1 || y_lo)) {
+      // 32-channel layer with a small dilation: halo-tile kernel with a resident filter (conv_h32.cu)
+      ConvH32Args q;
+      memset(&q, 0, sizeof(q));
+      q.scale = scale; q.shift = shift;
+      q.yh = (__half*)y_hi; q.yl = (__half*)y_lo;
+      q.n_out = d->n; q.OH = p.OH; q.OW = p.OW; q.cout = 32; q.act = d->act; q.terms = terms;
+      q.ntaps = 9;
+      for (int t = 0; t < 9; ++t) {
+        q.tz[t] = 0; q.ty[t] = (short)((t / 3) * d->dilation); q.tx[t] = (short)((t % 3) * d->dilation); q.tw[t] = (short)t;
+      }
+      q.hw = 8 + 2 * d->dilation; q.hh = 16 + 2 * d->dilation; q.hd = 1;
+      q.ox = -d->dilation; q.oy = -d->dilation;
+      const int rc = conv_h32_launch(h, (const __half*)x_hi, (const __half*)x_lo, (const __half*)w_hi,
+                                     (const __half*)w_lo, d->w, d->h, d->n, 9, q, st);
+      if (rc != DSIN_ERR_UNSUPPORTED) return rc;
+    }
     const bool use_pairs = (d->flags & DSIN_CONV_NO_CTA_PAIR) == 0;
     if (use_pairs && terms == 1 && !(d->flags & DSIN_CONV_NO_WEIGHT_STATIONARY) && k == 3 && d->stride == 1 &&
         d->dilation == 1 && dil_x == 1 && d->cin == 128 && d->cout == 128 && y_hi && !y_lo && !y_f32 && !res1_lo &&

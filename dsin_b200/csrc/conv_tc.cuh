@@ -61,3 +61,24 @@ struct ConvH3Args {
 };
 int conv_h3_launch(dsin_handle_t h, const __half* x_hi, const __half* x_lo, const __half* w_hi, const __half* w_lo,
                    const ConvH3Args& a, cudaStream_t st);
+
+// 32-channel layers on a halo tile with a resident filter (conv_h32.cu): SI-Net 3x3 layers with dilation <= 4 and the
+// (2,3,3) masked 3-D convolutions of the probability model.
+struct ConvH32Args {
+  const float* scale;
+  const float* shift;
+  __half *yh, *yl;   // split-fp16 output (cout == 32; yl may be NULL), or
+  float* yf;         // fp32 output (n_out, OH, OW, cout)
+  const float* r1f;  // optional cropped fp32 residual volume (3-D mode), read at +offsets
+  int r1_d, r1_oh, r1_ow, r1_dz, r1_dy, r1_dx, r1_c;
+  int n_out;         // output images (2-D: n; 3-D: vols * Do)
+  int dout, din;     // 3-D: Do, D -- output image n reads input images (n / Do) * D + n % Do + tz; 2-D: 0, 0
+  int OH, OW, cout, act, terms;
+  int ntaps;
+  short tz[18], ty[18], tx[18], tw[18];  // tap offsets inside the halo box (pixels), weight slab index
+  int hw, hh, hd;    // halo box extent (pixels, rows, depth slices)
+  int ox, oy;        // halo origin relative to the tile origin (-dilation for SAME, 0 for VALID)
+  int tiles_w, tiles_h, total_tiles, w_plane, w_region, a_plane, na;  // filled by conv_h32_launch
+};
+int conv_h32_launch(dsin_handle_t h, const __half* x_hi, const __half* x_lo, const __half* w_hi, const __half* w_lo,
+                    int W, int H, int ND, int wtaps, const ConvH32Args& a, cudaStream_t st);

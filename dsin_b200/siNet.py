@@ -17,6 +17,7 @@ from . import ops, synth
 # that tests can compare the forms against each other; the product never changes them.
 PAIR = True
 PAIR_SHARED = True
+HALO_MAX_RATE = 4
 
 
 class SiNet(object):
@@ -90,7 +91,9 @@ class SiNet(object):
             self._tc_first = ops.ConvTC(self._first_padded)
         use_pair = PAIR and ww % 2 == 0 and ww // 2 >= 16
         for li, tcl in enumerate([self._tc_first] + self._tc[:-1]):
-            if use_pair and li in self._pair:
+            # dilation <= 4: the plain 32-channel layer runs on the halo-tile kernel (csrc/conv_h32.cu); larger
+            # dilations have no halo worth loading and run tap by tap in the pixel-pair form (128-byte TMA rows)
+            if use_pair and li in self._pair and self.RATES[li] > HALO_MAX_RATE:
                 key = (li, PAIR_SHARED)
                 if key not in self._pair_tc:
                     rate = self.RATES[li]

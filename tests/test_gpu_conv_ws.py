@@ -114,3 +114,30 @@ def test_conv_h3_matches_float64_and_is_closer_than_the_single_accumulator_kerne
     assert float(e_h3.max()) < 1e-5 * scale_ref
     assert float(e_st.max()) < 1e-5 * scale_ref
     assert float(e_h3.pow(2).mean().sqrt()) <= 1.05 * float(e_st.pow(2).mean().sqrt())
+
+
+# ----------------------------------------------------------------------------- 32-channel halo kernel (conv_h32.cu)
+@pytest.mark.parametrize("terms,tol", [(3, 1e-5), (1, 4e-3)])
+@pytest.mark.parametrize("dil", [1, 2, 4])
+@pytest.mark.parametrize("shape", [(2, 40, 48), (1, 37, 52), (1, 320, 1224)])
+def test_conv_h32_sinet_layers_match_float64_and_streaming_kernel(shape, dil, terms, tol):
+    """SI-Net 3x3 32->32 layers with dilation 1/2/4, bias + LeakyReLU (src/siNet.py:9-10,31-34,39): halo-tile kernel vs
+    float64 on the operands it consumed and vs the tap-streaming kernel."""
+    from dsin_b200 import ops
+    n, hh, ww = shape
+    rng = np.random.default_rng(7 * dil + hh)
+    x = rng.standard_normal((n, 32, hh, ww)).astype(np.float32)
+    w = (rng.standard_normal((3, 3, 32, 32)) / np.sqrt(9 * 32)).astype(np.float32)
+    bias = (0.3 * rng.standard_normal(32)).astype(np.float32)
+    tcl = ops.ConvTC(ops.ConvLayer(w, None, bias, dilation=dil, act=ops.ACT_LRELU02))
+    xs = ops.f32_to_split(_nhwc(torch.tensor(x).cuda()), with_lo=terms == 3)
+    got = ops.conv_tc(xs, tcl, terms=terms)
+    old = ops.conv_tc(xs, tcl, terms=terms, flags=ops.CONV_NO_HALO)
+    got = ops.split_to_f32(*got).permute(0, 3, 1, 2).cpu().double()
+    old = ops.split_to_f32(*old).permute(0, 3, 1, 2).cpu().double()
+    xq = ops.split_to_f32(*xs).permute(0, 3, 1, 2).cpu().double()
+    ref = O.conv2d_same(xq, w.astype(np.float64), dilation=dil) + torch.tensor(bias).double().view(1, -1, 1, 1)
+    ref = torch.maximum(0.2 * ref, ref)
+    scale_ref = max(1.0, float(ref.abs().max()))
+    assert float((got - ref).abs().max()) < tol * scale_ref
+    assert float((got - old).abs().max()) < 2 * tol * scale_ref
