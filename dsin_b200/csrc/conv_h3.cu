@@ -113,6 +113,9 @@ conv_h3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant_
   cluster_sync_all();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  // everything above is independent of the previous layer; its output (our input, our residuals) is read from here on
+  pdl_wait();
+  pdl_launch_dependents();
   const int pairs = (p.total_tiles + 1) / 2;
   const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
@@ -368,7 +371,9 @@ int conv_h3_launch(dsin_handle_t h, const __half* x_hi, const __half* x_lo, cons
   const int pairs = (p.total_tiles + 1) / 2;
   int clusters = h->sm_count / 2;
   if (clusters > pairs) clusters = pairs;
-  conv_h3_kernel<<<2 * clusters, NTHREADS, SMEM_BYTES, st>>>(txh, txl, twh, twl, tyh, tyl, p);
+  if (launch_pdl(conv_h3_kernel, dim3(2 * clusters), dim3(NTHREADS), SMEM_BYTES, st, txh, txl, twh, twl, tyh, tyl, p) !=
+      cudaSuccess)
+    return dsin_fail(h, DSIN_ERR_CUDA, "%s: launch failed", __func__);
   DSIN_LAUNCHED(h);
   return DSIN_OK;
 }

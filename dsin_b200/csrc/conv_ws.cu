@@ -102,17 +102,22 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   cluster_sync_all();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  const int pairs = (p.total_tiles + 1) / 2;
-  const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (both CTAs)
-    if (elect_one()) {  // this CTA's half of the filter, once
+  if (warp == 0) {  // this CTA's half of the filter, once -- it does not depend on the previous layer either
+    if (elect_one()) {
       if (leader) mbar_expect_tx(wfull, 2u * (uint32_t)W_BYTES);
       for (int s = 0; s < 18; ++s)
         tma2_load_2d(wsm + s * W_SLAB, &tm_w, wfull, (s & 1) * 64, (s >> 1) * 128 + (int)rank * 64);
     }
     __syncwarp();
+  }
+  // everything above is independent of the previous layer; its output (our input, our residuals) is read from here on
+  pdl_wait();
+  pdl_launch_dependents();
+  const int pairs = (p.total_tiles + 1) / 2;
+  const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
     int stage = 0;
     uint32_t phase = 0;
     for (int pi = cid; pi < pairs; pi += nclusters) {
@@ -306,7 +311,8 @@ int conv_ws_launch(dsin_handle_t h, const __half* x, const __half* w_packed, con
   const int pairs = (p.total_tiles + 1) / 2;
   int clusters = h->sm_count / 2;
   if (clusters > pairs) clusters = pairs;
-  conv_ws_kernel<<<2 * clusters, 320, SMEM_BYTES, st>>>(tx, tw, ty, p);
+  if (launch_pdl(conv_ws_kernel, dim3(2 * clusters), dim3(320), SMEM_BYTES, st, tx, tw, ty, p) != cudaSuccess)
+    return dsin_fail(h, DSIN_ERR_CUDA, "%s: launch failed", __func__);
   DSIN_LAUNCHED(h);
   return DSIN_OK;
 }

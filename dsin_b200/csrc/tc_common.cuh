@@ -3,6 +3,7 @@
 // and host-side tensor-map encoding through the runtime's driver entry point.
 #pragma once
 #include <cuda.h>
+#include <utility>
 #include "common.cuh"
 
 namespace tc {
@@ -166,6 +167,14 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, in
                : "memory");
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Consecutive layers are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs may
+// start (barrier init, TMEM allocation, tensor-map prefetch, filter loads -- nothing that depends on the previous
+// layer) on SMs the previous kernel has already left; pdl_wait() then blocks until the previous grid has completed and
+// its writes are visible.  pdl_launch_dependents() is the previous kernel's permission for that early start.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ CTA pairs (cta_group::2)
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the pair's leader CTA
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -278,6 +287,24 @@ static inline bool encode_tmap(CUtensorMap* m, CUtensorMapDataType dt, int rank,
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   return fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Launch `kernel` so that it may overlap the tail of the kernel before it in the stream (see pdl_wait above).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 }  // namespace tc

@@ -43,13 +43,14 @@ def main():
         ae.pc_imgcomp.bitcost(out["qbar"], out["symbols"], False, pad_value=ae.pc_imgcomp.auto_pad_value(ae.ae_imgcomp),
                               terms=pol.probclass)
     if "quant" in what:
-        ae.ae_imgcomp.encode(xd[:1], terms=pol.enc_x) if "enc1" in what else None
         z33 = torch.randn(2 * B, 40, 153, 33, device="cuda")
         ops.heatmap_quantize(z33, ae.ae_imgcomp._centers, full=True)
     if "sif" in what:
         match_images(x_dec, y_nhwc, y_dec, 20, 24, True)
-    if "trunk" in what:
-        ae.ae_imgcomp.decode(out["qbar"], terms=pol.dec)
+    if "trunk" in what:   # decoder of 2B images: the fp16-operand trunk (conv_ws) + from_bn / h12 / h13
+        ae.ae_imgcomp.decode(torch.cat([out["qbar"], out["qbar"]]), terms=pol.dec)
+    if "enc" in what:     # encoder of 2B images: the fp32-class trunk (conv_h3) + h1 / h2 / to_bn + quantiser
+        ae.ae_imgcomp.encode(torch.cat([yd, xd]), terms=pol.enc_x)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
 
