@@ -428,6 +428,8 @@ def run_ours(args, rank, world, local_rank):
                 "frac": ach / pk["tf_sust"], "traffic": traffic,
                 "peak_source": pk["src"] + " bf16 dense sustained (fp16 shares the rate)",
                 "mma_terms_per_product": mma_terms, "frac_counting_issued_mma_work": mma_terms * ach / pk["tf_sust"],
+                "peak_of_this_precision_mode": pk["tf_sust"] / mma_terms,
+                "frac_of_mode_peak": mma_terms * ach / pk["tf_sust"],
                 "share_of_step": v["ms"] / tot_prof_ms,
                 "avg_launch_ms": v["ms"] / v["launches"],
                 "timing": "CUDA events around every launch of this kernel on the launching stream, eager pass of "

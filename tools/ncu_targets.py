@@ -37,6 +37,8 @@ def main():
     y_nhwc = ops.nchw_to_nhwc(yd)
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
+    if "step" in what:    # one whole eager step (every kernel of the timed path, in order)
+        ae.reconstruct_device(xd, yd)
     if "sinet" in what:
         ae._siNet.fused(x_dec, y_syn, terms=pol.sinet)
     if "probclass" in what:
