@@ -15,10 +15,15 @@
 // strip -- overlapping windows, no im2col.  One K=16 MMA step consumes two pixels of one layer; a layer
 // is 24 px = 12 steps; 8 layers per patch (96 MMAs of 128x256x16 per tile).
 // Patches are pre-centred per patch (q - mean_q) before the fp16 rounding, which removes the large
-// cancellation in the Pearson numerator; the coarse score error is ~1e-4.  Each work unit (image,
-// patch tile, 8 correlation rows) keeps the 4 best coarse candidates per patch; a second kernel rescored
-// every candidate within DELTA of the coarse best with the reference's exact arithmetic (fp32 data,
-// fp64 dot product, literal fp32 Pearson algebra, exact fp64->fp32 prior) and takes the first maximum.
+// cancellation in the Pearson numerator; the coarse score error is ~1e-4.  Candidates: per (patch, work unit, column
+// half) = "group" (4 correlation rows x every other 128-column block) the epilogue keeps the TOPK = 4 best coarse
+// scores.  sif_rescore_kernel rescored every kept position within DELTA of the patch's overall coarse best with the
+// reference's exact arithmetic (fp32 data, fp64 dot product, literal fp32 Pearson algebra, exact fp64->fp32 prior)
+// and takes the first maximum.  Measured on smooth synthetic and on decoded images (tools/sif_candidates_probe.py): the
+// number of positions within DELTA of the best is 1 for most patches and <= 8 per patch, <= 6 per group, on the smoothest
+// inputs tried.  If a group's 4th-best is itself within DELTA, positions that were not kept may qualify too: the group
+// goes on a work list and sif_exhaustive_kernel rescored ALL its positions exactly, one CTA per listed group (a first
+// version did this inside the per-patch warp and a handful of such patches cost milliseconds of tail latency).
 #include "sif_common.cuh"
 #include "tc_common.cuh"
 
@@ -37,14 +42,14 @@ constexpr int B_BYTES = STRIP_PIX * 16; // 4480
 constexpr int STAGE_BYTES = A_BYTES + 5120;
 constexpr int STAGES = 4;
 constexpr int ROWS_PER_UNIT = 4;  // finer work units: static round-robin imbalance < 1 %
-constexpr int TOPK = 4;
+constexpr int TOPK = 4;  // candidates kept per group
 constexpr float DELTA = 2e-3f;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * TN * 8 + 1024 /*align*/ + 512 /*barriers*/;
 
 struct SifP {
   const float4* ystat;   // (n,hp,wp): sum_y, mean_y, den_y, sum_y2
   const float4* pinfo;   // (n,P): sum of fp16 centred patch, rsqrt(den_x), cy', cx'
-  float2* cand;          // (n,P,rgroups,2,TOPK): coarse score, position index (as int bits)
+  float2* cand;          // (n,P,rgroups,2,TOPK): coarse score (descending), position index (as int bits; -1 = empty)
   int n, hp, wp, P, ptiles, rgroups, jtiles, total_units, use_mask;
   float kh, kw;          // -4/sigma_h^2, -4/sigma_w^2 (exp2 form of exp(-4 ln2 t))
 };
@@ -164,8 +169,8 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------------------ epilogue warps 2..9
-    // Two warps per TMEM lane quarter; each scores half of the tile's 256 positions for its 32 patches
-    // and keeps its own running top-4 (flushed per work unit, so a patch has 8 candidates per unit).
+    // Two warps per TMEM lane quarter; each scores half of the tile's 256 positions for its 32 patches and keeps the
+    // TOPK best of its group in registers (written out per work unit).
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int et = (warp - 2) * 32 + lane;  // 0..255 among epilogue threads
@@ -177,7 +182,7 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       const bool pvalid = pch < p.P;
       float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
       if (pvalid) pi = p.pinfo[(size_t)img * p.P + pch];
-      float bs0 = -INFINITY, bs1 = -INFINITY, bs2 = -INFINITY, bs3 = -INFINITY;
+      float bs0 = -INFINITY, bs1 = -INFINITY, bs2 = -INFINITY, bs3 = -INFINITY;  // the group's 4 best, descending
       int bi0 = -1, bi1 = -1, bi2 = -1, bi3 = -1;
       const int i1 = min(p.hp, (rg + 1) * ROWS_PER_UNIT);
       for (int i = rg * ROWS_PER_UNIT; i < i1; ++i) {
@@ -220,9 +225,10 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 float dw = (float)(j0 + c) - pi.w;
                 s *= ex2_approx(p.kw * dw * dw);
               }
-              const bool pass = pvalid && c < nvalid && s > bs3;
+              // a flat window (den_y <= 0: ps.y == 0) is NaN / inf in the exact arithmetic and is never a candidate
+              const bool pass = pvalid && c < nvalid && ps.y > 0.f && s > bs3;
               if (__any_sync(0xffffffffu, pass)) {  // rare after warm-up; the branch is warp-uniform
-                if (pass) {
+                if (pass) {  // strict >: among equal scores the earlier position stays ahead
                   const int idx = i * p.wp + j0 + c;
                   if (s > bs0) {
                     bs3 = bs2; bi3 = bi2; bs2 = bs1; bi2 = bi1; bs1 = bs0; bi1 = bi0; bs0 = s; bi0 = idx;
@@ -330,71 +336,140 @@ __global__ void __launch_bounds__(256) sif_pack_strip_kernel(const float* __rest
 }
 
 // ---- exact rescoring: one warp per (image, patch) ------------------------------------------------
-__global__ void sif_rescore_kernel(const float2* __restrict__ cand, int ncand, const float* __restrict__ q,
+// exact masked score of one position from its window's dot product: the reference's literal fp32 algebra, exact prior
+__device__ __forceinline__ unsigned long long sif_exact_key(double dot, const float* __restrict__ ystat,
+                                                            const float* __restrict__ ps, int img, int pch, int i,
+                                                            int j, int hh, int ww, int ph, int pw, int use_mask) {
+  const int wp = ww - pw + 1, hp = hh - ph + 1;
+  const float4 ys = reinterpret_cast<const float4*>(ystat)[((int64_t)img * hp + i) * wp + j];
+  float s = sif_pearson((float)dot, ys.x, ys.y, ys.z, ps[0], ps[2], ps[3], (float)(ph * pw * 3));
+  if (use_mask) s = __fmul_rn(s, sif_mask_exact(pch, i, j, hh, ww, ph, pw));
+  return sif_pack(s, (unsigned)(i * wp + j));
+}
+
+__global__ void sif_rescore_kernel(const float2* __restrict__ cand, int ngroups, const float* __restrict__ q,
                                    const float* __restrict__ r, const float* __restrict__ pstat,
-                                   const float* __restrict__ ystat, int n, int hh, int ww, int ph, int pw,
-                                   int use_mask, unsigned long long* __restrict__ keys) {
+                                   const float* __restrict__ ystat, int n, int hh, int ww, int ph, int pw, int use_mask,
+                                   unsigned long long* __restrict__ keys, int2* __restrict__ worklist,
+                                   int* __restrict__ work_count, int work_cap) {
   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
   const int lane = threadIdx.x % 32;
   const int P = (hh / ph) * (ww / pw);
   if (wid >= (int64_t)n * P) return;
   const int img = (int)(wid / P), pch = (int)(wid % P);
-  const int wp = ww - pw + 1, hp = hh - ph + 1;
+  const int wp = ww - pw + 1;
   const int kdim = ph * pw * 3, krow = pw * 3;
-  const float2* cp = cand + wid * ncand;
-  float best = -INFINITY;
-  for (int c = lane; c < ncand; c += 32) best = fmaxf(best, cp[c].x);
-  for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
-  const float thr = best - DELTA;
+  const float2* cp = cand + wid * (int64_t)ngroups * TOPK;
   const float* qp = q + wid * kdim;
   const float* ps = pstat + wid * 4;
-  unsigned long long key = 0ull;
-  // exact masked score of position (i, j): fp32 data, fp64 dot product, the reference's literal fp32 algebra
-  auto rescore = [&](int i, int j) {
-    const float* rp = r + (((int64_t)img * hh + i) * ww + j) * 3;
-    double acc = 0.0;
-    for (int k = lane; k < kdim; k += 32) {
-      const int dy = k / krow, kk = k - dy * krow;
-      acc += (double)qp[k] * (double)__ldg(rp + (int64_t)dy * ww * 3 + kk);
-    }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      const float4 ys = reinterpret_cast<const float4*>(ystat)[((int64_t)img * hp + i) * wp + j];
-      float s = sif_pearson((float)acc, ys.x, ys.y, ys.z, ps[0], ps[2], ps[3], (float)kdim);
-      if (use_mask) s = __fmul_rn(s, sif_mask_exact(pch, i, j, hh, ww, ph, pw));
-      const unsigned long long k2 = sif_pack(s, (unsigned)(i * wp + j));
-      key = k2 > key ? k2 : key;
-    }
-  };
-  if (ps[3] < 0.f) {  // den_x < 0 (a flat patch whose fp32 variance rounded below zero): sqrt(den) is NaN at every
-    if (lane == 0) keys[wid] = 0ull;  // position, a NaN never wins tf.argmax, all-NaN -> index 0 (sif_common.cuh)
+  if (!(ps[3] > 0.f)) {  // den_x <= 0 (a flat patch): sqrt(den) is NaN / the quotient infinite at every position; a NaN
+    if (lane == 0) keys[wid] = 0ull;  // never wins tf.argmax and all-NaN -> index 0 (sif_common.cuh)
     return;
   }
-  for (int c = 0; c < ncand; ++c) {
-    const float2 cv = cp[c];
-    const int idx = __float_as_int(cv.y);
-    if (!(cv.x >= thr) || idx < 0) continue;  // warp-uniform
-    rescore(idx / wp, idx % wp);
-  }
-  // Overflow: a (work unit, column half) keeps only its TOPK best coarse scores.  If even the weakest kept one is
-  // within DELTA of the global coarse best, positions that were NOT kept may qualify too (periodic textures, flat
-  // regions: many near-equal scores) -- then every position of that group is rescored exactly.  Rare; costs
-  // ~0.3 ms per group and patch when it happens.
-  for (int g = 0; g < ncand / TOPK; ++g) {
-    const float2 weakest = cp[g * TOPK + TOPK - 1];
-    if (!(weakest.x >= thr) || __float_as_int(weakest.y) < 0) continue;  // warp-uniform
-    const int rg = g >> 1, half = g & 1;
-    const int i1 = min(hp, (rg + 1) * ROWS_PER_UNIT);
-    for (int i = rg * ROWS_PER_UNIT; i < i1; ++i)
-      for (int j = 0; j < wp; ++j)
-        if (((j & (TN - 1)) >> 7) == half) rescore(i, j);
+  float best = -INFINITY;
+  for (int g = lane; g < ngroups; g += 32) best = fmaxf(best, cp[(int64_t)g * TOPK].x);  // lists are sorted
+  for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+  const float thr = best - DELTA;
+  unsigned long long key = 0ull;
+  for (int g0 = 0; g0 < ngroups; g0 += 32) {
+    const int g = g0 + lane;
+    float gbest = -INFINITY, gweak = -INFINITY;
+    if (g < ngroups) {
+      gbest = cp[(int64_t)g * TOPK].x;
+      gweak = cp[(int64_t)g * TOPK + TOPK - 1].x;
+    }
+    unsigned live = __ballot_sync(0xffffffffu, gbest >= thr);  // groups that hold a position within DELTA of the best
+    // ... and whose weakest kept candidate qualifies too: positions that were NOT kept may qualify as well
+    if (g < ngroups && gweak >= thr) {
+      const int slot = atomicAdd(work_count, 1);
+      if (slot < work_cap) worklist[slot] = make_int2((int)wid, g);
+    }
+    while (live) {
+      const int src = __ffs(live) - 1;
+      live &= live - 1;
+      const int gg = g0 + src;
+      for (int e = 0; e < TOPK; ++e) {  // one position at a time, the dot product spread over the lanes (fp64)
+        const float2 cv = cp[(int64_t)gg * TOPK + e];
+        const int idx = __float_as_int(cv.y);
+        if (!(cv.x >= thr) || idx < 0) break;  // sorted: nothing further qualifies (warp-uniform)
+        const int i = idx / wp, j = idx % wp;
+        const float* rp = r + (((int64_t)img * hh + i) * ww + j) * 3;
+        double acc = 0.0;
+        for (int k = lane; k < kdim; k += 32) {
+          const int dy = k / krow, kk = k - dy * krow;
+          acc += (double)qp[k] * (double)__ldg(rp + (int64_t)dy * ww * 3 + kk);
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+          const unsigned long long k2 = sif_exact_key(acc, ystat, ps, img, pch, i, j, hh, ww, ph, pw, use_mask);
+          key = k2 > key ? k2 : key;
+        }
+      }
+    }
   }
   if (lane == 0) keys[wid] = key;
 }
 
+// One CTA per listed (patch, group): every position of the group (4 correlation rows x every other 128-column block),
+// one position per thread (coalesced window reads, two fp64 chains), merged into the patch's key with a 64-bit max.
+// The list has room for every group of every patch, so nothing is ever dropped.
+__global__ void __launch_bounds__(128) sif_exhaustive_kernel(const int2* __restrict__ worklist,
+                                                             const int* __restrict__ work_count, int work_cap,
+                                                             const float* __restrict__ q, const float* __restrict__ r,
+                                                             const float* __restrict__ pstat,
+                                                             const float* __restrict__ ystat, int n, int hh, int ww,
+                                                             int ph, int pw, int use_mask,
+                                                             unsigned long long* __restrict__ keys) {
+  const int count = min(*work_count, work_cap);
+  __shared__ unsigned long long s_key[4];
+  const int P = (hh / ph) * (ww / pw);
+  const int wp = ww - pw + 1, hp = hh - ph + 1;
+  const int krow = pw * 3;
+  for (int item = blockIdx.x; item < count; item += gridDim.x) {
+    const int2 w = worklist[item];
+    const int wid = w.x, gg = w.y;
+    const int img = wid / P, pch = wid % P;
+    const float* qp = q + (int64_t)wid * (ph * krow);
+    const float* ps = pstat + (int64_t)wid * 4;
+    const int rg = gg >> 1, half = gg & 1;
+    const int i0 = rg * ROWS_PER_UNIT, i1 = min(hp, i0 + ROWS_PER_UNIT);
+    unsigned long long key = 0ull;
+    for (int i = i0; i < i1; ++i)
+      for (int jb = half * (TN / 2); jb < wp; jb += TN) {  // this half's 128-column blocks: one position per thread
+        const int j = jb + (int)threadIdx.x;
+        if (j >= wp) continue;
+        const float* rp = r + (((int64_t)img * hh + i) * ww + j) * 3;
+        double a0 = 0.0, a1 = 0.0;
+        for (int dy = 0; dy < ph; ++dy) {
+          const float* rr = rp + (int64_t)dy * ww * 3;
+          const float* qq = qp + dy * krow;
+          for (int kk = 0; kk < krow; kk += 2) {
+            a0 += (double)__ldg(qq + kk) * (double)__ldg(rr + kk);
+            a1 += (double)__ldg(qq + kk + 1) * (double)__ldg(rr + kk + 1);
+          }
+        }
+        const unsigned long long k2 = sif_exact_key(a0 + a1, ystat, ps, img, pch, i, j, hh, ww, ph, pw, use_mask);
+        key = k2 > key ? k2 : key;
+      }
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+      key = other > key ? other : key;
+    }
+    if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long k = s_key[0];
+      for (int t = 1; t < 4; ++t) k = s_key[t] > k ? s_key[t] : k;
+      atomicMax(keys + wid, k);
+    }
+    __syncthreads();
+  }
+}
+
 struct Layout {
-  int64_t q2, strip, pinfo, cand, total;
-  int ptiles, rgroups, jtiles, ncand;
+  int64_t q2, strip, pinfo, cand, work, total;
+  int work_cap;
+  int ptiles, rgroups, jtiles, ngroups;
 };
 
 Layout make_layout(int n, int hh, int ww, int ph, int pw) {
@@ -403,13 +478,15 @@ Layout make_layout(int n, int hh, int ww, int ph, int pw) {
   L.ptiles = (P + 127) / 128;
   L.rgroups = (hp + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
   L.jtiles = (wp + TN - 1) / TN;
-  L.ncand = L.rgroups * 2 * TOPK;  // two epilogue warps (column halves) per patch
+  L.ngroups = L.rgroups * 2;  // two epilogue warps (column halves) per patch and work unit
   auto up = [](int64_t v) { return (v + 1023) / 1024 * 1024; };
   L.q2 = 0;
   L.strip = up((int64_t)n * P * KQ * 2);
   L.pinfo = L.strip + up((int64_t)n * PAIRS * (hh - ph + 1) * ww * 16);
   L.cand = L.pinfo + up((int64_t)n * P * 16);
-  L.total = L.cand + up((int64_t)n * P * L.ncand * 8);
+  L.work = L.cand + up((int64_t)n * P * L.ngroups * TOPK * 8);  // [count (16 B)][work_cap x int2]
+  L.work_cap = n * P * L.ngroups;  // every group of every patch fits
+  L.total = L.work + up(16 + (int64_t)L.work_cap * 8);
   return L;
 }
 
@@ -471,8 +548,16 @@ int sif_tc_match(dsin_handle_t h, const float* q, const float* r, const float* p
   const int grid = p.total_units < h->sm_count ? p.total_units : h->sm_count;
   sif_tc_kernel<<<grid, 320, SMEM_BYTES, st>>>(tm_q, tm_s, p);
   DSIN_LAUNCHED(h);
-  sif_rescore_kernel<<<(unsigned)((np * 32 + 255) / 256), 256, 0, st>>>(cand, L.ncand, q, r, pstat, ystat, n, hh, ww,
-                                                                   ph, pw, use_mask, keys);
+  int* work_count = (int*)(base + L.work);
+  int2* worklist = (int2*)(base + L.work + 16);
+  if (cudaMemsetAsync(work_count, 0, 16, st) != cudaSuccess) return dsin_fail(h, DSIN_ERR_CUDA, "%s: memset failed", __func__);
+  sif_rescore_kernel<<<(unsigned)((np * 32 + 255) / 256), 256, 0, st>>>(cand, L.ngroups, q, r, pstat, ystat, n, hh, ww,
+                                                                   ph, pw, use_mask, keys, worklist, work_count,
+                                                                   L.work_cap);
+  DSIN_LAUNCHED(h);
+  // groups whose candidate list may have been too short: all their positions, one CTA per group (usually none)
+  sif_exhaustive_kernel<<<h->sm_count * 8, 128, 0, st>>>(worklist, work_count, L.work_cap, q, r, pstat, ystat, n, hh, ww, ph,
+                                                       pw, use_mask, keys);
   DSIN_LAUNCHED(h);
   return DSIN_OK;
 }
