@@ -2,6 +2,7 @@
 
     AE(ae_config, pc_config, encoder, decoder, siFinder, SI_full_img, siNet, cur_dir)
     siNet_get_reconstructed(x, y) -> (y_dec, y_syn, x_dec, x_with_si, bpp)     src/AE.py:132-148
+    siNet_validate(x, y) -> loss_test (forward pass + loss reductions)         src/AE.py:76-99,120-131
     create_y_dec(y)                                                            src/AE.py:150-152
     load_model(path) / save_model(path)                                        src/AE.py:154-175
 
@@ -9,7 +10,7 @@ Differences (documented in DESIGN.md): inputs may hold B >= 1 pairs (the referen
 hard-wired to batch 1, src/AE.py:26) -- each pair is processed with batch-1 semantics and bpp is
 the batch aggregate of bits.bitcost_to_bpp; the two autoencoder passes (on y and on x) run as
 one batch of 2B images; weights are read from a TF-V2 checkpoint (tf_checkpoint.py, no TensorFlow) or an
-.npz keyed by the TF variable names; training entry points raise NotImplementedError.
+.npz keyed by the TF variable names; the training step (siNet_update) raises NotImplementedError.
 """
 from __future__ import annotations
 
@@ -19,6 +20,7 @@ import numpy as np
 import torch
 
 from . import autoencoder_imgcomp as autoencoder
+from . import Distortions_imgcomp as Distortions
 from . import bits_imgcomp as bits
 from . import ops
 from . import precision as precision_policy
@@ -148,10 +150,49 @@ class AE(object):
         return mean.reshape(3, 1, 1), var.reshape(3, 1, 1)
 
     def siNet_update(self, x, y):
-        raise NotImplementedError("training is out of scope for dsin_b200 (inference hot path only)")
+        raise NotImplementedError("the training step (gradients, optimiser) is not built; dsin_b200 has the forward "
+                                  "passes only: siNet_get_reconstructed and siNet_validate")
 
     def siNet_validate(self, x, y):
-        raise NotImplementedError("training is out of scope for dsin_b200 (inference hot path only)")
+        """x, y: (B,3,H,W) uint8 / uint8-valued arrays -> the scalar validation loss `loss_test` of src/AE.py:120-131:
+        one forward pass in inference mode, then
+            (1 - si_weight) * d_loss_scaled(x, x_dec) + beta * max(H_soft - H_target, 0) + reg
+            + si_weight * mean|x - x_with_si|                      (src/AE.py:76-99, src/Distortions_imgcomp.py:113-146).
+        The forward pass is the one siNet_get_reconstructed runs (same kernels, same CUDA graphs); the reductions are
+        one more launch pair (csrc/loss.cu).  The components are kept in `self.last_loss`."""
+        xs, ys = self._stage(x, "x"), self._stage(y, "y")
+        if self.use_cuda_graph:
+            out = self.replay_device(xs, ys)
+            xd = self._graphs[(xs.shape[0], xs.shape[2], xs.shape[3])]["x"]
+        else:
+            xd = xs.to(torch.float32)
+            out = self.reconstruct_device(xd, ys.to(torch.float32))
+        self.last = out
+        loss, comps = self.validation_loss_device(xd, out)
+        self.last_loss = comps
+        return loss
+
+    def validation_loss_device(self, x, out):
+        """x (B,3,H,W) fp32 CUDA tensor and the dict reconstruct_device / replay_device returned for it ->
+        (loss_test, components)."""
+        c = self.ae_config
+        terms = ops.validation_terms(x, out["x_dec"].contiguous(), None if self.AE_only else out["x_with_si"],
+                                     out["bits"], out["heatmap"], squared=Distortions.squared_distortion(c))
+        t = terms.cpu().numpy()  # (B, 4) float64 per-image sums; synchronises the stream
+        B = x.shape[0]
+        img_elems, sym_elems = x.numel() // B, out["bits"].numel() // B
+        d = Distortions.distortion_to_minimize(c, t[:, 0], img_elems)
+        H_real = np.float32(t[:, 2].sum() / float(B * sym_elems))
+        H_mask = np.float32(t[:, 3].sum() / float(B * sym_elems))
+        w = np.float32(self.si_weight)
+        total, H_real, pc_comps, ae_comps = Distortions.get_loss(c, self.ae_imgcomp, self.pc_imgcomp,
+                                                                 np.float32(np.float32(1) - w) * d, H_real, H_mask)
+        # tf.losses.absolute_difference: sum of |x - x_with_si| over the number of elements (src/AE.py:94)
+        loss_siNet = np.float32(0) if self.AE_only else np.float32(t[:, 1].sum() / float(B * img_elems))
+        loss_test = np.float32(total + np.float32(w * loss_siNet))
+        comps = dict(pc_comps + ae_comps)
+        comps.update({"d_loss": d, "total_loss_test": total, "loss_siNet": loss_siNet, "loss_test": loss_test})
+        return float(loss_test), comps
 
     # ------------------------------------------------------------------ host <-> device staging
     def _stage(self, a, slot):
@@ -205,15 +246,16 @@ class AE(object):
         P = self.precision
         if P.enc_x == P.enc_y:
             z = self._encode(torch.cat([y, x], dim=0), self.ae_imgcomp, is_training=False, terms=P.enc_x)
-            qall, qx, sx, sy = z.qbar, z.qbar[B:], z.symbols[B:], z.symbols[:B]
+            qall, qx, sx, sy, hx = z.qbar, z.qbar[B:], z.symbols[B:], z.symbols[:B], z.heatmap[B:]
         else:  # the two encoder passes run at different operand precision: two launches per layer
             zy = self._encode(y, self.ae_imgcomp, is_training=False, terms=P.enc_y)
             zx = self._encode(x, self.ae_imgcomp, is_training=False, terms=P.enc_x)
-            qall, qx, sx, sy = self._cat_qbar(zy.qbar, zx.qbar), zx.qbar, zx.symbols, zy.symbols
+            qall, qx, sx, sy, hx = self._cat_qbar(zy.qbar, zx.qbar), zx.qbar, zx.symbols, zy.symbols, zx.heatmap
         dec = self._decode(qall, self.ae_imgcomp, is_training=False, terms=P.dec)
         bc = self.pc_imgcomp.bitcost(qx, sx, is_training=False,
                                      pad_value=self.pc_imgcomp.auto_pad_value(self.ae_imgcomp), terms=P.probclass)
-        return {"dec": dec, "symbols": sx, "symbols_y": sy, "qbar": qx, "bits": bc, "bits_sum": bc._dsin_sum}
+        return {"dec": dec, "symbols": sx, "symbols_y": sy, "qbar": qx, "bits": bc, "bits_sum": bc._dsin_sum,
+                "heatmap": hx}
 
     @staticmethod
     def _cat_qbar(qa, qb):

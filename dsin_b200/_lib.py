@@ -59,6 +59,7 @@ SIGNATURES = {
     "dsin_sif_match": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "dsin_msssim_workspace_bytes": (_I64, [_I, _I, _I, _I, _I]),
     "dsin_msssim": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "dsin_validation_terms": (_I, [_P, _P, _P, _P, _P, _P, _I, _I64, _I64, _I, _P, _P]),
     "dsin_sif_gather": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "dsin_pc_codec_workspace_bytes": (_I64, [_I, _I, _I, _I]),
     "dsin_pc_encode": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _I64, _P, _P, _P, _P]),

@@ -14,11 +14,15 @@ import numpy as np
 import torch
 
 from . import ops, synth
+from .Distortions_imgcomp import regularization_loss
 
 EncoderOutput = namedtuple("EncoderOutput", ["qbar", "qhard", "symbols", "z", "heatmap"])
 
 BN_EPS = np.float32(1e-5)
 arch_param_n = 128
+SCOPE_AE = "autoencoder"                 # src/autoencoder_imgcomp.py:21-23
+SCOPE_AE_ENC = SCOPE_AE + "/encoder"
+SCOPE_AE_DEC = SCOPE_AE + "/decoder"
 
 # Every conv of the encoder/decoder runs on tcgen05 (csrc/conv_tc*.cu).  `terms` (precision.py) says how many MMAs
 # build one product: 3 = split-fp16 hi*hi + hi*lo + lo*hi (fp32-class), 1 = fp16 operands.  There is no other
@@ -46,6 +50,7 @@ class _Network(object):
         self._centers = None
         self.layers = {}
         self._tc_layers = {}
+        self._variables = {}
         self.device = "cuda"
 
     @staticmethod
@@ -56,6 +61,15 @@ class _Network(object):
         if self._centers is None:
             raise ValueError("Call load_weights(...) before trying to access centers")
         return self._centers
+
+    def encoder_regularization_loss(self):
+        """includes centers regularization (src/autoencoder_imgcomp.py:79-82); see Distortions_imgcomp for the
+        scope rule that makes this 0.0 in the graph src/AE.py builds."""
+        return regularization_loss(self._variables, SCOPE_AE_ENC, self.config.regularization_factor,
+                                   self.config.regularization_factor_centers)
+
+    def decoder_regularization_loss(self):
+        return regularization_loss(self._variables, SCOPE_AE_DEC, self.config.regularization_factor)
 
     # -- weights ---------------------------------------------------------------------------
     def _conv(self, W, scope, stride=1, relu=True, transposed=False, post=ops.POST_NONE):
@@ -127,6 +141,7 @@ class _CVPR(_Network):
     def load_weights(self, W):
         B = self.config.arch_param_B
         E, D = synth.ENC, synth.DEC
+        self._variables = W
         self._tc_layers = {}
         self._h13_tc = None
         self._centers = torch.from_numpy(np.ascontiguousarray(W[E + "centers"], np.float32)).to(self.device)

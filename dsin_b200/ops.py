@@ -430,6 +430,22 @@ def sif_gather(y_nhwc, row, col, ph, pw):
     return out
 
 
+def validation_terms(x, x_dec, x_with_si, bitcost, heatmap, squared=False):
+    """fp32 CUDA tensors x, x_dec, x_with_si (n, ...) (x_with_si may be None), bitcost, heatmap (n, ...) (heatmap may
+    be None) -> (n, 4) float64 CUDA tensor of per-image sums [dist(x_dec, x), |x - x_with_si|, bc, bc * heatmap]."""
+    h = handle()
+    n = x.shape[0]
+    img_elems, sym_elems = x.numel() // n, bitcost.numel() // n
+    assert x_dec.shape == x.shape and (x_with_si is None or x_with_si.shape == x.shape)
+    assert heatmap is None or heatmap.shape == bitcost.shape
+    out = torch.empty((n, 4), dtype=torch.float64, device=x.device)
+    h.check(h.lib.dsin_validation_terms(h.ptr, _p(_chk(x)), _p(_chk(x_dec)),
+                                        None if x_with_si is None else _p(_chk(x_with_si)), _p(_chk(bitcost)),
+                                        None if heatmap is None else _p(_chk(heatmap)), n, img_elems, sym_elems,
+                                        1 if squared else 0, _p(out), _stream()))
+    return out
+
+
 MSSSIM_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)  # ms_ssim_np_imgcomp.py:91-92
 
 

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import bitstream, ops, synth
+from .Distortions_imgcomp import regularization_loss
 
 
 # The two 24->24 layers and the head run on tcgen05; the all-CUDA-core kernel (ops.probclass_bits) is the
@@ -60,6 +61,7 @@ class _ResShallow(object):
 
     def load_weights(self, W):
         P = synth.PC
+        self._variables = W
         out = []
         for name, mask in (("conv3d_conv0_mask", self.first_mask), ("res1/conv3d_conv1_mask", self.other_mask),
                            ("res1/conv3d_conv2_mask", self.other_mask), ("conv3d_conv2_mask", self.other_mask)):
@@ -80,6 +82,14 @@ class _ResShallow(object):
             packed = np.ascontiguousarray(np.stack([w[kd, kh, kw] for kd, kh, kw in taps]))
             self._codec.append(torch.from_numpy(packed).to(self.device))
             self._codec.append(torch.from_numpy(np.ascontiguousarray(W[P + name + "/biases"], np.float32)).to(self.device))
+
+    def regularization_loss(self):
+        """src/probclass_imgcomp.py:88-95,115-119: None unless the config sets a regularization_factor; then
+        factor * sum of l2_loss over the conv3d weights that `tf.losses.get_regularization_loss(scope='probclass3d')`
+        selects (prefix rule, see Distortions_imgcomp.regularization_loss)."""
+        if self.config.regularization_factor is None:
+            return None
+        return regularization_loss(self._variables, self._PROBCLASS_SCOPE, self.config.regularization_factor)
 
     def bitcost(self, q, target_symbols, is_training=False, pad_value=0, terms=3):
         """q: qbar NCHW fp32, target_symbols NCHW int64 -> bits per symbol NCHW.  The fp64

@@ -208,6 +208,17 @@ int64_t dsin_msssim_workspace_bytes(int groups, int batch, int height, int width
 int dsin_msssim(dsin_handle_t h, const float* img1, const float* img2, int groups, int batch, int height,
                 int width, int depth, double* out_g52, void* workspace, void* stream);
 
+/* ---- validation loss terms (forward half) -----------------------------------------------
+ * Replaces the reductions of AE.siNet_validate's loss_test (src/AE.py:76-99,120-131):
+ * Distortions.get_mae_per_img / get_mse_per_img (src/Distortions_imgcomp.py:68-101), get_loss's reduce_mean(bc) and
+ * reduce_mean(bc * heatmap) (:119-121) and tf.losses.absolute_difference(x, x_with_si) (src/AE.py:94).
+ * x, x_dec, x_with_si: fp32 (n, img_elems) (x_with_si may be NULL: AE_only); bitcost, heatmap: fp32 (n, sym_elems)
+ * (heatmap may be NULL); squared != 0 sums (x_dec - x)^2 instead of |x_dec - x|.
+ * terms_n4: (n, 4) doubles = per image [sum dist(x_dec, x), sum |x - x_with_si|, sum bc, sum bc * heatmap]. */
+int dsin_validation_terms(dsin_handle_t h, const float* x, const float* x_dec, const float* x_with_si,
+                          const float* bitcost, const float* heatmap, int n, int64_t img_elems,
+                          int64_t sym_elems, int squared, double* terms_n4, void* stream);
+
 /* ---- PC1 entropy coder: real bitstreams from the probability model --------------------------
  * The reference has no coder, only its building blocks (src/probclass_imgcomp.py:361-482: per-symbol frequencies
  * from the context model, causal order).  The byte-exact format is specified in oracle/pc_codec.c.

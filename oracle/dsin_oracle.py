@@ -484,6 +484,84 @@ def reconstruct(x_np, y_np, W, dtype=torch.float32, ph=20, pw=24, use_mask=True,
 
 
 # --------------------------------------------------------------------------------------
+# validation loss (src/AE.py:71-99,120-131: siNet_validate -> loss_test)
+# --------------------------------------------------------------------------------------
+ValidationLoss = namedtuple("ValidationLoss", ["loss", "d_loss_scaled", "pc_loss", "reg_loss", "loss_siNet",
+                                               "H_real", "H_mask"])
+
+
+def regularization_loss(W, scope, factor, factor_centers):
+    """tf.losses.get_regularization_loss(scope) as the reference calls it (src/autoencoder_imgcomp.py:80-86): the
+    REGULARIZATION_LOSSES collection is filtered with re.match(scope, op.name), i.e. a PREFIX match on the full op name.
+    slim adds factor * l2_loss(w) = factor * sum(w^2) / 2 for every conv / deconv `weights` variable created inside
+    _building_ctx (src/autoencoder_imgcomp.py:98-104) and factor_centers * l2_loss(centers) for the centres
+    (src/quantizer_imgcomp.py:18-24); op names start with the variable's full name.  In the graph AE.py builds, those
+    names start with 'encoder/encoder_body/...' resp. 'decoder/...' (src/AE.py:51-56) while the scopes asked for are
+    'autoencoder/encoder' and 'autoencoder/decoder' (src/autoencoder_imgcomp.py:21-23): nothing matches, the sum is
+    0.0.  The rule is restated in full so that a differently scoped weight file behaves as TF would."""
+    import re
+    rx = re.compile(scope)
+    total = 0.0
+    for name in sorted(W):
+        if not rx.match(name):
+            continue
+        w = np.asarray(W[name], dtype=np.float64)
+        if name.endswith("/weights") and factor:
+            total += float(factor) * 0.5 * float(np.sum(w * w))
+        elif name.endswith("/centers") and factor_centers:
+            total += float(factor_centers) * 0.5 * float(np.sum(w * w))
+    return total
+
+
+def distortion_to_minimize(x, x_out, kind="mae", K_psnr=100.0):
+    """Distortions(config, x, x_out, is_training=True).d_loss_scaled (src/Distortions_imgcomp.py:7-56,68-118): per-image
+    means, then the batch mean.  With is_training=True the distortion that is minimised is NOT cast to integers (:19-21)."""
+    if kind == "mae":
+        return torch.abs(x_out - x).mean(dim=(1, 2, 3)).mean()
+    if kind == "mse":
+        return torch.square(x_out - x).mean(dim=(1, 2, 3)).mean()
+    if kind == "psnr":
+        mse = torch.square(x_out - x).mean(dim=(1, 2, 3))
+        return K_psnr - (10.0 * (torch.log(255.0 * 255.0 / mse) / math.log(10.0))).mean()
+    raise ValueError("distortion_to_minimize = %r is not restated (the shipped config uses mae)" % (kind,))
+
+
+def get_loss(d_loss_scaled, bc, heatmap, beta, H_target, reg_enc=0.0, reg_dec=0.0, reg_probclass=0.0):
+    """src/Distortions_imgcomp.py:113-146 -> (total_loss, H_real, H_mask, pc_loss)."""
+    H_real = bc.mean()
+    H_mask = (bc * heatmap).mean()
+    H_soft = 0.5 * (H_mask + H_real)
+    pc_loss = beta * torch.clamp(H_soft - H_target, min=0.0)
+    reg_loss = reg_probclass + reg_enc + reg_dec
+    return d_loss_scaled + pc_loss + reg_loss, H_real, H_mask, pc_loss
+
+
+def validation_loss(x_np, y_np, W, dtype=torch.float32, ph=20, pw=24, use_mask=True, si_weight=0.7, beta=500.0,
+                    H_target=0.04, distortion="mae", K_psnr=100.0, regularization_factor=0.005,
+                    regularization_factor_centers=0.1, force_symbols_x=None, force_symbols_y=None, force_rowcol=None):
+    """AE.siNet_validate (src/AE.py:120-131): one forward pass in inference mode -> the scalar loss_test =
+    (1 - si_weight) * d_loss_scaled + beta * max(0.5 * (mean(bc * heatmap) + mean(bc)) - H_target, 0) + reg
+    + si_weight * mean|x - x_with_si|  (src/AE.py:76-99)."""
+    x = _t(x_np, dtype)
+    y = _t(y_np, dtype)
+    with torch.no_grad():
+        _ency, y_dec = ae_pass(y, W, force_symbols_y)
+        encx, x_dec = ae_pass(x, W, force_symbols_x)
+        bc = probclass_bitcost(encx.qbar, encx.symbols, W)
+        y_syn, _row, _col, _best = si_full_img(x_dec, y, y_dec, ph, pw, use_mask, force_rowcol)
+        x_with_si = denormalize(si_net(torch.cat([normalize(x_dec), normalize(y_syn)], dim=1), W))
+        d = distortion_to_minimize(x, x_dec, distortion, K_psnr)
+        reg_enc = regularization_loss(W, "autoencoder/encoder", regularization_factor, regularization_factor_centers)
+        reg_dec = regularization_loss(W, "autoencoder/decoder", regularization_factor, 0.0)
+        total, H_real, H_mask, pc_loss = get_loss((1.0 - si_weight) * d, bc, encx.heatmap, beta, H_target,
+                                                  reg_enc, reg_dec)  # probclass: regularization_factor = None
+        l_si = torch.abs(x - x_with_si).mean()  # tf.losses.absolute_difference: sum / number of elements
+        loss = total + si_weight * l_si
+    return ValidationLoss(float(loss), float(d), float(pc_loss), reg_enc + reg_dec, float(l_si), float(H_real),
+                          float(H_mask))
+
+
+# --------------------------------------------------------------------------------------
 # BN calibration of random-init weights (SURVEY section 7 hard part 6) -- test helper
 # --------------------------------------------------------------------------------------
 def calibrate_bn(W, x_np, dtype=torch.float32):

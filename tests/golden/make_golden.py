@@ -245,6 +245,11 @@ def _make_tf():
         reduce_sum=lambda v, axis=None, name=None: _T(np.sum(_raw(v), axis=axis, dtype=np.float32)),
         reduce_prod=lambda v: _T(np.prod(_raw(v))),
         to_float=lambda v: _T(np.float32(_raw(v))),
+        int32=_DType(np.int32),
+        cast=lambda v, dt: _T(np.asarray(_raw(v)).astype(dt.np_dtype)),  # float -> int32 truncates toward zero, as TF
+        constant=lambda v, dtype=None, name=None: _T(np.asarray(v, dtype=(dtype.np_dtype if dtype else None))),
+        reduce_mean=lambda v, axis=None, name=None: _T(np.mean(np.asarray(_raw(v)), dtype=np.float32,
+                                                               axis=(tuple(axis) if isinstance(axis, list) else axis))),
     )
 
 
@@ -295,10 +300,48 @@ def make_tf_pieces():
     np.savez_compressed(os.path.join(OUT, "tf_pieces_golden.npz"), **out)
 
 
+def make_loss_pieces():
+    """The loss arithmetic of siNet_validate (src/AE.py:76-99): the reference's own Distortions class and get_loss
+    (src/Distortions_imgcomp.py:7-56,68-146) executed on the numpy stand-in, for all three restated distortions."""
+    tree = ast.parse(open(os.path.join(REF, "Distortions_imgcomp.py")).read())
+    body = [n for n in tree.body if (isinstance(n, ast.ClassDef) and n.name == "Distortions")
+            or (isinstance(n, ast.FunctionDef) and n.name == "get_loss")]
+    tf = _make_tf()
+    helpers = types.SimpleNamespace(  # fjcommon.tf_helpers.log10: log(x) / log(10)
+        log10=lambda v: _T((np.log(_raw(v)) / np.float32(np.log(10.0))).astype(np.float32)),
+        list_without_None=lambda *a: [v for v in a if v is not None])
+    ns = {"np": np, "tf": tf, "tf_helpers": helpers}
+    exec(compile(ast.Module(body=body, type_ignores=[]), "Distortions_imgcomp.py", "exec"), ns)
+    rng = np.random.default_rng(31)
+    out = {}
+    x = rng.integers(0, 256, size=(3, 3, 16, 24)).astype(np.float32)
+    x_out = np.clip(x + 6.0 * rng.standard_normal(x.shape), 0, 255).astype(np.float32)
+    bc = rng.uniform(0, 4, size=(3, 32, 2, 3)).astype(np.float32)
+    hm = np.clip(rng.uniform(-0.5, 1.5, size=bc.shape), 0, 1).astype(np.float32)
+    out["x"], out["x_out"], out["bc"], out["heatmap"] = x, x_out, bc, hm
+    regs = {"enc": np.float32(0.375), "dec": np.float32(0.125)}
+    ae = types.SimpleNamespace(encoder_regularization_loss=lambda: _T(regs["enc"]),
+                               decoder_regularization_loss=lambda: _T(regs["dec"]))
+    pc = types.SimpleNamespace(regularization_loss=lambda: None)
+    for name in ("mae", "mse", "psnr"):
+        for h_target in (0.04, 2.5):  # the rate term active / clamped at zero
+            cfg = types.SimpleNamespace(distortion_to_minimize=name, K_psnr=100, K_ms_ssim=5000, H_target=h_target, beta=500)
+            d = ns["Distortions"](cfg, _T(x), _T(x_out), is_training=True)
+            out["d_%s" % name] = np.float32(d.d_loss_scaled.a)
+            total, h_real, pc_comps, _ae_comps = ns["get_loss"](cfg, ae, pc, _T(np.float32(0.3)) * d.d_loss_scaled, _T(bc), _T(hm))
+            out["total_%s_%g" % (name, h_target)] = np.float32(total.a)
+            out["H_real"] = np.float32(h_real.a)
+            out["H_mask"] = np.float32(dict(pc_comps)["H_mask"].a)
+    out["reg_enc"], out["reg_dec"] = regs["enc"], regs["dec"]
+    np.savez_compressed(os.path.join(OUT, "loss_pieces_golden.npz"), **out)
+
+
 if __name__ == "__main__":
+    make_loss_pieces()
     make_masks()
     make_msssim()
     make_model_pieces()
     make_tf_pieces()
-    for f in ("mask_golden.npz", "msssim_golden.npz", "model_pieces_golden.npz", "tf_pieces_golden.npz"):
+    for f in ("mask_golden.npz", "msssim_golden.npz", "model_pieces_golden.npz", "tf_pieces_golden.npz",
+              "loss_pieces_golden.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)))

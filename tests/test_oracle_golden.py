@@ -227,3 +227,67 @@ def test_oracle_matches_reference_elementwise_functions(golden_dir):
     assert float((qsoft - torch.tensor(g["q_soft"])).abs().max()) <= 5e-7
     n_pix = int(np.prod(g["bc_input_shape"])) // 3
     assert float(O.bitcost_to_bpp(torch.tensor(g["bc"]), n_pix)) == pytest.approx(float(g["bpp"]), rel=2e-7)
+
+
+def test_loss_arithmetic_matches_reference(golden_dir):
+    """siNet_validate's loss arithmetic (src/AE.py:76-99): the oracle's restatement AND the product's host-side float32
+    arithmetic (dsin_b200/Distortions_imgcomp.py, fed with float64 sums like the ones csrc/loss.cu produces) against the
+    reference's own Distortions class and get_loss, executed on the numpy stand-in for TF (make_golden.make_loss_pieces)."""
+    import types
+
+    from dsin_b200 import Distortions_imgcomp as D
+    g = np.load(os.path.join(golden_dir, "loss_pieces_golden.npz"))
+    x, xo, bc, hm = (g[k] for k in ("x", "x_out", "bc", "heatmap"))
+    tx, txo, tbc, thm = (torch.tensor(a) for a in (x, xo, bc, hm))
+    n = x.shape[0]
+    img_elems = x[0].size
+    ae = types.SimpleNamespace(encoder_regularization_loss=lambda: np.float32(g["reg_enc"]),
+                               decoder_regularization_loss=lambda: np.float32(g["reg_dec"]))
+    pc = types.SimpleNamespace(regularization_loss=lambda: None)
+    H_real = np.float32(bc.astype(np.float64).sum() / bc.size)
+    H_mask = np.float32((bc.astype(np.float32) * hm).astype(np.float64).sum() / bc.size)
+    assert abs(float(H_real) - float(g["H_real"])) <= 2e-7 and abs(float(H_mask) - float(g["H_mask"])) <= 2e-7
+    for kind in ("mae", "mse", "psnr"):
+        d_or = O.distortion_to_minimize(tx, txo, kind, 100.0)
+        assert abs(float(d_or) - float(g["d_" + kind])) <= 2e-6 * abs(float(g["d_" + kind]))
+        diff = (xo.astype(np.float32) - x).astype(np.float64)
+        sums = (np.abs(diff) if kind == "mae" else diff * diff).reshape(n, -1).sum(1)
+        cfg = types.SimpleNamespace(distortion_to_minimize=kind, K_psnr=100, beta=500, H_target=0.04)
+        assert D.squared_distortion(cfg) == (kind != "mae")
+        d_pr = D.distortion_to_minimize(cfg, sums, img_elems)
+        assert abs(float(d_pr) - float(g["d_" + kind])) <= 2e-6 * abs(float(g["d_" + kind]))
+        for h_target in (0.04, 2.5):
+            want = float(g["total_%s_%g" % (kind, h_target)])
+            tot, hr, hk, _pl = O.get_loss(np.float32(0.3) * d_or, tbc, thm, 500.0, h_target, float(g["reg_enc"]),
+                                          float(g["reg_dec"]))
+            assert abs(float(tot) - want) <= 2e-6 * abs(want)
+            assert abs(float(hr) - float(g["H_real"])) <= 2e-7 and abs(float(hk) - float(g["H_mask"])) <= 2e-7
+            cfg.H_target = h_target
+            tot_p, hr_p, pc_comps, ae_comps = D.get_loss(cfg, ae, pc, np.float32(0.3) * d_pr, H_real, H_mask)
+            assert abs(float(tot_p) - want) <= 2e-6 * abs(want)
+            assert dict(pc_comps)["reg"] == 0 and abs(float(dict(ae_comps)["reg_enc_dec"]) - 0.5) < 1e-7
+    with pytest.raises(NotImplementedError):
+        D.distortion_to_minimize(types.SimpleNamespace(distortion_to_minimize="ms_ssim"), [1.0], 10)
+
+
+def test_regularization_scope_rule():
+    """tf.losses.get_regularization_loss(scope) filters by re.match on the op name (a prefix match): with the variable
+    names of the graph src/AE.py builds nothing matches 'autoencoder/encoder' / 'autoencoder/decoder' and the term is
+    0.0; weights that DO live under those scopes are summed as factor * sum(w^2) / 2 (+ the centres' term)."""
+    from dsin_b200 import Distortions_imgcomp as D
+    from dsin_b200 import synth
+    W = synth.make_weights(0)
+    for fn in (D.regularization_loss, O.regularization_loss):
+        assert float(fn(W, "autoencoder/encoder", 0.005, 0.1)) == 0.0
+        assert float(fn(W, "autoencoder/decoder", 0.005, 0.0)) == 0.0
+        renamed = {k[len("encoder/encoder_body/encoder_body/"):]: v for k, v in W.items() if k.startswith(O.ENC)}
+        want = 0.0
+        for k, v in renamed.items():
+            v = np.asarray(v, np.float64)
+            if k.endswith("/weights"):
+                want += 0.005 * 0.5 * float((v * v).sum())
+            elif k.endswith("/centers"):
+                want += 0.1 * 0.5 * float((v * v).sum())
+        got = float(fn(renamed, "autoencoder/encoder", 0.005, 0.1))
+        assert want > 0 and abs(got - want) <= 1e-6 * want
+        assert float(fn(renamed, "autoencoder/decoder", 0.005, 0.0)) == 0.0
