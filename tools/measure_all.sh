@@ -26,8 +26,8 @@ ncu)
   timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -o $out/${tag}_full python tools/ncu_targets.py --what sinet,probclass,quant,sif,trunk,enc > $out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
   ;;
 sanitizer)
-  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_conv_ws.py tests/test_gpu_codec.py tests/test_gpu_sifinder_edge.py -q -x -k "shape0 or shape2 or all_nan or identical or small or random" > $out/${tag}_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -5 $out/${tag}_memcheck.log
-  timeout 900 compute-sanitizer --tool racecheck --error-exitcode 1 python -m pytest tests/test_gpu_conv_ws.py tests/test_gpu_codec.py -q -x -k "shape0 or shape2 or small or random" > $out/${tag}_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -5 $out/${tag}_racecheck.log
+  timeout 480 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_conv_ws.py tests/test_gpu_codec.py tests/test_gpu_sifinder_edge.py -q -x -k "shape0 or shape2 or all_nan or identical or small or random" > $out/${tag}_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -5 $out/${tag}_memcheck.log
+  timeout 480 compute-sanitizer --tool racecheck --error-exitcode 1 python -m pytest tests/test_gpu_conv_ws.py tests/test_gpu_codec.py -q -x -k "shape0 or shape2 or small or random" > $out/${tag}_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -5 $out/${tag}_racecheck.log
   ;;
 esac
 done
