@@ -420,7 +420,10 @@ def run_ours(args, rank, world, local_rank):
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(name, {}).get("bytes_per_launch")
+                ent = json.load(f).get(name, {})
+            # the captures were taken at 8 pairs per launch; bytes scale with the pairs one launch processes
+            if ent.get("bytes_per_launch"):
+                traffic = ent["bytes_per_launch"] * micro[0] / float(ent.get("pairs_per_launch", 8))
         except Exception:  # noqa: BLE001
             pass
         mma_terms = 3 if name.startswith("tc3_") else 1

@@ -42,8 +42,8 @@ conv_h32_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* wsm = smem;                                    // [plane][tap][NPAD rows][64 B]
   uint8_t* a_tiles = wsm + p.w_region;                    // na x [plane][halo box]
-  uint8_t* stg = a_tiles + p.na * PLANES * p.a_plane;     // 4 warps x [hi 2 KB, lo 2 KB]
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(stg + 4 * 4096);
+  uint8_t* stg = a_tiles + p.na * PLANES * p.a_plane;     // 2 buffers x 4 quarters x [hi 2 KB, lo 2 KB]
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(stg + 8 * 4096);
   uint64_t* empty_a = full_a + 4;
   uint64_t* tfull = empty_a + 4;
   uint64_t* tempty = tfull + 2;
@@ -168,8 +168,7 @@ conv_h32_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
     const bool has_cols = half * 16 < NPAD;
     const int row = q * 32 + lane;
     const int rl = row >> 3, cl = row & 7;
-    const uint32_t stg_hi = smem_u32(stg + q * 4096);
-    const uint32_t stg_lo = stg_hi + 2048;
+    const uint32_t stg_q = smem_u32(stg + q * 4096);  // + (it & 1) * 16 KB: tiles alternate between two staging buffers
     const uint32_t row_off = (uint32_t)lane * 64u;
     const int sw = (lane >> 1) & 3;  // 64-byte swizzle: 16-byte piece j of pixel p sits at ((j ^ ((p >> 1) & 3)) * 16)
     const bool split_out = p.yh != nullptr;
@@ -191,9 +190,12 @@ conv_h32_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
       const int oy = th * TR + rl, ox = tw * TC + cl;
       const bool valid = oy < p.OH && ox < p.OW;
       const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
+      const uint32_t stg_hi = stg_q + (uint32_t)(acc * 4 * 4096);
+      const uint32_t stg_lo = stg_hi + 2048;
       if (split_out) {
-        // the previous tile's stores (issued by half 0) have finished reading the staging block
-        if (half == 0 && lane == 0) tma_store_wait_read();
+        // the stores of the tile before the previous one (issued by half 0) have finished reading this staging buffer,
+        // the previous tile's may still be in flight
+        if (half == 0 && lane == 0) tma_store_wait_read1();
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       }
       mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u);
@@ -251,8 +253,9 @@ conv_h32_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant
         fence_proxy_async();  // this thread's generic-proxy writes to the staging block -> visible to the TMA stores
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
         if (half == 0 && lane == 0) {  // the stores clip rows / pixels past the output
-          tma_store_4d(&tm_yh, stg_hi, 0, tw * TC, th * TR + q * 4, n);
-          if (p.yl) tma_store_4d(&tm_yl, stg_lo, 0, tw * TC, th * TR + q * 4, n);
+          tma_store_4d_issue(&tm_yh, stg_hi, 0, tw * TC, th * TR + q * 4, n);
+          if (p.yl) tma_store_4d_issue(&tm_yl, stg_lo, 0, tw * TC, th * TR + q * 4, n);
+          tma_store_commit();  // one group per tile
         }
       }
     }
@@ -300,7 +303,7 @@ int conv_h32_launch(dsin_handle_t h, const __half* x_hi, const __half* x_lo, con
   p.w_plane = 0;
   p.w_region = (planes * a.ntaps * npad * 64 + 1023) / 1024 * 1024;
   p.a_plane = (a.hd * a.hh * a.hw * 64 + 1023) / 1024 * 1024;
-  const int fixed = p.w_region + 4 * 4096 + 1024 /*barriers, scale/shift*/ + 1024 /*alignment*/;
+  const int fixed = p.w_region + 8 * 4096 + 1024 /*barriers, scale/shift*/ + 1024 /*alignment*/;
   int na = (227 * 1024 - fixed) / (planes * p.a_plane);
   if (na > 4) na = 4;
   if (na < 2) return dsin_fail(h, DSIN_ERR_UNSUPPORTED, "%s: halo tile too large for two pipeline stages", __func__);

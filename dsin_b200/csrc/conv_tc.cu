@@ -618,6 +618,19 @@ extern "C" int dsin_conv2d_tc(dsin_handle_t h, const dsin_conv_desc_t* d, int te
                                      (const __half*)w_lo, d->w, d->h, d->n, 9, q, st);
       if (rc != DSIN_ERR_UNSUPPORTED) return rc;
     }
+    if (!(d->flags & (DSIN_CONV_NO_HALO | DSIN_CONV_PAIR_SHARED)) && k == 3 && d->stride == 1 && d->cin == 32 &&
+        d->cout == 32 && d->dilation > 4 && dil_x == d->dilation && y_hi && !y_f32 && !res1_hi && !res2_hi &&
+        d->post == DSIN_POST_NONE && (terms == 1 || y_lo)) {
+      // 32-channel layer with a large dilation: row-band kernel (conv_dil.cu)
+      ConvDilArgs q;
+      memset(&q, 0, sizeof(q));
+      q.scale = scale; q.shift = shift;
+      q.yh = (__half*)y_hi; q.yl = (__half*)y_lo;
+      q.n = d->n; q.H = d->h; q.W = d->w; q.dil = d->dilation; q.act = d->act; q.terms = terms;
+      const int rc = conv_dil_launch(h, (const __half*)x_hi, (const __half*)x_lo, (const __half*)w_hi,
+                                     (const __half*)w_lo, q, st);
+      if (rc != DSIN_ERR_UNSUPPORTED) return rc;
+    }
     const bool use_pairs = (d->flags & DSIN_CONV_NO_CTA_PAIR) == 0;
     if (use_pairs && terms == 1 && !(d->flags & DSIN_CONV_NO_WEIGHT_STATIONARY) && k == 3 && d->stride == 1 &&
         d->dilation == 1 && dil_x == 1 && d->cin == 128 && d->cout == 128 && y_hi && !y_lo && !y_f32 && !res1_lo &&

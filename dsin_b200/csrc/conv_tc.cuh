@@ -80,5 +80,16 @@ struct ConvH32Args {
   int ox, oy;        // halo origin relative to the tile origin (-dilation for SAME, 0 for VALID)
   int tiles_w, tiles_h, total_tiles, w_plane, w_region, a_plane, na;  // filled by conv_h32_launch
 };
+// conv_dil.cu: 3x3, 32 -> 32 channels, stride 1, SAME, dilation `dil` >= 1 (meant for >= 8), split-fp16 or fp16 output
+struct ConvDilArgs {
+  const float* scale;
+  const float* shift;
+  __half *yh, *yl;  // output planes (n, H, W, 32); yl may be NULL with terms == 1
+  int n, H, W, dil, act, terms;
+  // filled by conv_dil_launch
+  int nbox, bw, a_plane, w_region, nb, tiles_w, phases, seg, nseg, total_units;
+};
+int conv_dil_launch(dsin_handle_t h, const __half* x_hi, const __half* x_lo, const __half* w_hi, const __half* w_lo,
+                    const ConvDilArgs& a, cudaStream_t st);
 int conv_h32_launch(dsin_handle_t h, const __half* x_hi, const __half* x_lo, const __half* w_hi, const __half* w_lo,
                     int W, int H, int ND, int wtaps, const ConvH32Args& a, cudaStream_t st);

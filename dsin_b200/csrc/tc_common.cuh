@@ -159,6 +159,17 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t smem
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// the same without the commit: several stores can form ONE bulk group (tma_store_commit), so that
+// tma_store_wait_read1() -- "all but the most recent group have finished reading shared memory" -- lets a kernel
+// alternate between two staging buffers and overlap a tile's stores with the next tile's epilogue
+__device__ __forceinline__ void tma_store_4d_issue(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {

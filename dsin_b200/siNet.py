@@ -12,9 +12,11 @@ import torch
 
 from . import ops, synth
 
-# Layer forms (all tcgen05, csrc/conv_tc.cu).  PAIR: the pixel-pair view (128-byte TMA rows) for the nine 3x3
-# layers; PAIR_SHARED: even dilations reuse the plain 32x32 slab for both pixels of a pair.  Module attributes so
-# that tests can compare the forms against each other; the product never changes them.
+# Layer forms (all tcgen05).  Dilation <= HALO_MAX_RATE: halo-tile kernel (csrc/conv_h32.cu); larger dilations: row-band
+# kernel (csrc/conv_dil.cu) when BAND, else the tap-streaming kernel (csrc/conv_tc.cu) in the pixel-pair view (PAIR:
+# 128-byte TMA rows; PAIR_SHARED: even dilations reuse the plain 32x32 slab for both pixels of a pair).  Module
+# attributes so that tests can compare the forms against each other; the product never changes them.
+BAND = True
 PAIR = True
 PAIR_SHARED = True
 HALO_MAX_RATE = 4
@@ -92,8 +94,8 @@ class SiNet(object):
         use_pair = PAIR and ww % 2 == 0 and ww // 2 >= 16
         for li, tcl in enumerate([self._tc_first] + self._tc[:-1]):
             # dilation <= 4: the plain 32-channel layer runs on the halo-tile kernel (csrc/conv_h32.cu); larger
-            # dilations have no halo worth loading and run tap by tap in the pixel-pair form (128-byte TMA rows)
-            if use_pair and li in self._pair and self.RATES[li] > HALO_MAX_RATE:
+            # dilations on the row-band kernel (csrc/conv_dil.cu) -- both chosen by dsin_conv2d_tc from the geometry
+            if not BAND and use_pair and li in self._pair and self.RATES[li] > HALO_MAX_RATE:
                 key = (li, PAIR_SHARED)
                 if key not in self._pair_tc:
                     rate = self.RATES[li]

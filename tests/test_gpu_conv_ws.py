@@ -141,3 +141,35 @@ def test_conv_h32_sinet_layers_match_float64_and_streaming_kernel(shape, dil, te
     scale_ref = max(1.0, float(ref.abs().max()))
     assert float((got - ref).abs().max()) < tol * scale_ref
     assert float((got - old).abs().max()) < 2 * tol * scale_ref
+
+
+# ----------------------------------------------------------------------------- 32-channel row-band kernel (conv_dil.cu)
+@pytest.mark.parametrize("terms,tol", [(3, 1e-5), (1, 4e-3)])
+@pytest.mark.parametrize("shape,dil", [((2, 40, 48), 8), ((1, 37, 56), 16), ((1, 64, 136), 8), ((1, 80, 144), 32),
+                                       ((1, 80, 144), 128), ((1, 320, 1224), 8), ((1, 320, 1224), 16),
+                                       ((1, 320, 1224), 64), ((2, 320, 1224), 128), ((1, 33, 264), 24)])
+def test_conv_dil_sinet_layers_match_float64_and_streaming_kernel(shape, dil, terms, tol):
+    """SI-Net 3x3 32->32 layers with dilation >= 8, bias + LeakyReLU (src/siNet.py:9-10,34-38): row-band kernel vs float64
+    on the operands it consumed and vs the tap-streaming kernel.  Covers images narrower than one 128-pixel tile, heights
+    below the dilation (every vertical neighbour outside the image), chains of one row, segments, and a dilation that is
+    not a multiple of 8."""
+    from dsin_b200 import ops
+    n, hh, ww = shape
+    rng = np.random.default_rng(11 * dil + hh)
+    x = rng.standard_normal((n, 32, hh, ww)).astype(np.float32)
+    w = (rng.standard_normal((3, 3, 32, 32)) / np.sqrt(9 * 32)).astype(np.float32)
+    bias = (0.3 * rng.standard_normal(32)).astype(np.float32)
+    tcl = ops.ConvTC(ops.ConvLayer(w, None, bias, dilation=dil, act=ops.ACT_LRELU02))
+    xs = ops.f32_to_split(_nhwc(torch.tensor(x).cuda()), with_lo=terms == 3)
+    l0 = ops.launch_count()
+    got = ops.conv_tc(xs, tcl, terms=terms)
+    assert ops.launch_count() - l0 == 1
+    old = ops.conv_tc(xs, tcl, terms=terms, flags=ops.CONV_NO_HALO)
+    got = ops.split_to_f32(*got).permute(0, 3, 1, 2).cpu().double()
+    old = ops.split_to_f32(*old).permute(0, 3, 1, 2).cpu().double()
+    xq = ops.split_to_f32(*xs).permute(0, 3, 1, 2).cpu().double()
+    ref = O.conv2d_same(xq, w.astype(np.float64), dilation=dil) + torch.tensor(bias).double().view(1, -1, 1, 1)
+    ref = torch.maximum(0.2 * ref, ref)
+    scale_ref = max(1.0, float(ref.abs().max()))
+    assert float((got - ref).abs().max()) < tol * scale_ref
+    assert float((got - old).abs().max()) < 2 * tol * scale_ref
