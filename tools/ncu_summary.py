@@ -17,7 +17,10 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max", "smsp__cycles_active.avg",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sectors_srcunit_tex_op_read.sum"]
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
+        # shared-memory wavefronts (128 B) fetched by the tensor core (MMA operands) and by load/store instructions
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 
 def launches(path):
