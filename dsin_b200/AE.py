@@ -30,6 +30,16 @@ from . import tf_checkpoint
 from .siFinder import GaussianPrior
 
 
+def _host_copy(dst, a):
+    """Contiguous numpy array -> pinned tensor of the same shape and dtype.  Copied as 8-byte words by torch's
+    multi-threaded copy when the size allows (a 1-byte-element copy_ is not vectorised, and numpy's assignment is one
+    memcpy thread: 75 MB of uint8 images per micro-batch of 32 pairs took 5 ms of the end-to-end call)."""
+    if a.nbytes >= (1 << 20) and a.nbytes % 8 == 0 and torch.get_num_threads() > 1:
+        dst.view(-1).view(torch.int64).copy_(torch.from_numpy(a.reshape(-1).view(np.int64)))
+    else:
+        dst.numpy()[...] = a
+
+
 class AE(object):
     def __init__(self, ae_config, pc_config, encoder, decoder, siFinder, SI_full_img, siNet, cur_dir,
                  weights=None, seed=0, device=None, precision=None):
@@ -205,7 +215,7 @@ class AE(object):
         if buf is None:
             buf = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
             self._pinned[key] = buf
-        buf.numpy()[...] = a
+        _host_copy(buf, a)
         return buf.to(self.device, non_blocking=True)
 
     def _to_device(self, a, slot):
@@ -230,14 +240,18 @@ class AE(object):
         return [b.numpy() for b in outs]
 
     # ------------------------------------------------------------------ inference
-    def reconstruct_device(self, x, y, on_decoded=None):
+    def reconstruct_device(self, x, y, on_decoded=None, on_found=None):
         """Device-resident variant: x, y (B,3,H,W) fp32 CUDA tensors -> dict of CUDA tensors.
-        on_decoded(dec) is called as soon as the decoder output (2B,3,H,W) = [y_dec; x_dec] is enqueued,
-        so a caller can start copying it out while the SI-Finder and SI-Net run."""
+        on_decoded(dec) is called as soon as the decoder output (2B,3,H,W) = [y_dec; x_dec] is enqueued and
+        on_found(y_syn) as soon as the SI-Finder's output is, so a caller can start copying them out while the
+        SI-Finder resp. the SI-Net run."""
         out = self._encode_decode(x, y)
         if on_decoded is not None:
             on_decoded(out["dec"])
-        out.update(self._side_information(out["dec"], y, x.shape[0]))
+        out.update(self._find_side_information(out["dec"], y, x.shape[0]))
+        if on_found is not None:
+            on_found(out["y_syn"])
+        out.update(self._fuse_side_information(out))
         return out
 
     def _encode_decode(self, x, y):
@@ -268,19 +282,20 @@ class AE(object):
 
     def replay_device(self, x, y):
         """reconstruct_device through the captured CUDA graphs: x, y (B,3,H,W) CUDA tensors (any dtype) are copied
-        into the captured input buffers, the two graphs are replayed, and the dict of STATIC output tensors is
+        into the captured input buffers, the three graphs are replayed, and the dict of STATIC output tensors is
         returned (overwritten by the next replay)."""
         st = self._graph_state(x.shape[0], x.shape[2], x.shape[3])
         st["x"].copy_(x)
         st["y"].copy_(y)
         st["g_head"].replay()
-        st["g_tail"].replay()
-        out = dict(st["head"])
-        out.update(st["tail"])
-        return out
+        st["g_find"].replay()
+        st["g_net"].replay()
+        return dict(st["out"])
 
     def _graph_state(self, B, H, W):
-        """Capture (once per shape) the two halves of the inference step as CUDA graphs over static buffers."""
+        """Capture (once per shape) the three segments of the inference step -- AE(y) + AE(x) + bit cost, SI-Finder,
+        SI-Net -- as CUDA graphs over static buffers (segments, so that each segment's outputs can be copied to the host
+        while the next one runs)."""
         key = (B, H, W)
         st = self._graphs.get(key)
         if st is not None:
@@ -295,12 +310,14 @@ class AE(object):
                 self.reconstruct_device(x, y)
         cur.wait_stream(side)
         torch.cuda.synchronize()
-        g_head, g_tail = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        g_head, g_find, g_net = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_head, capture_error_mode="thread_local"):
-            head = self._encode_decode(x, y)
-        with torch.cuda.graph(g_tail, pool=g_head.pool(), capture_error_mode="thread_local"):
-            tail = self._side_information(head["dec"], y, B)
-        st = {"x": x, "y": y, "g_head": g_head, "g_tail": g_tail, "head": head, "tail": tail}
+            out = self._encode_decode(x, y)
+        with torch.cuda.graph(g_find, pool=g_head.pool(), capture_error_mode="thread_local"):
+            out.update(self._find_side_information(out["dec"], y, B))
+        with torch.cuda.graph(g_net, pool=g_head.pool(), capture_error_mode="thread_local"):
+            out.update(self._fuse_side_information(out))
+        st = {"x": x, "y": y, "g_head": g_head, "g_find": g_find, "g_net": g_net, "out": out}
         self._graphs[key] = st
         return st
 
@@ -315,16 +332,30 @@ class AE(object):
         return self._side_information(dec, y, B)
 
     def _side_information(self, dec, y, B):
+        out = self._find_side_information(dec, y, B)
+        out.update(self._fuse_side_information(out))
+        return out
+
+    def _find_side_information(self, dec, y, B):
+        """SI-Finder (src/AE.py:58-61): y_syn = the side image re-assembled from the best-matching patches."""
         dec_nhwc = dec._dsin_nhwc
         y_dec, x_dec = dec[:B], dec[B:]
         y_dec._dsin_nhwc, x_dec._dsin_nhwc = dec_nhwc[:B], dec_nhwc[B:]
         out = {"y_dec": y_dec, "x_dec": x_dec}
         if self.AE_only:
             out["y_syn"] = torch.zeros_like(y)
-            out["x_with_si"] = torch.zeros_like(y)
             return out
         y_syn, _ncc, _arg, _q, _r, row, col, _xp, _yp = self._SI_full_img(
             x_dec, y, self.mask, self._y_patch_h, self._y_patch_w, self.ae_config, y_dec)
+        out.update({"y_syn": y_syn, "row": row, "col": col, "best": getattr(y_syn, "_dsin_best", None)})
+        return out
+
+    def _fuse_side_information(self, found):
+        """SI-Net (src/AE.py:63-69) on what _find_side_information returned -> {"x_with_si": ...}."""
+        x_dec, y_syn = found["x_dec"], found["y_syn"]
+        if self.AE_only:
+            return {"x_with_si": torch.zeros_like(y_syn)}
+        y = y_syn
         fused = getattr(self._siNet, "fused", None)
         if fused is not None and hasattr(y_syn, "_dsin_nhwc"):
             x_with_si = fused(x_dec._dsin_nhwc, y_syn._dsin_nhwc, terms=self.precision.sinet)
@@ -334,9 +365,7 @@ class AE(object):
             s = torch.from_numpy(np.sqrt(var + 1e-10).astype(np.float32)).to(y.device)
             cat = torch.cat([(x_dec - m) / s, (y_syn - m) / s], dim=1)
             x_with_si = self._siNet(cat) * s + m
-        out.update({"y_syn": y_syn, "x_with_si": x_with_si, "row": row, "col": col,
-                    "best": getattr(y_syn, "_dsin_best", None)})
-        return out
+        return {"x_with_si": x_with_si}
 
     def _pinned_out(self, name, shape, dtype):
         key = ("out", name, self._ring, tuple(shape))
@@ -351,7 +380,7 @@ class AE(object):
         src/DataProvider.py:197-199) or float32 holding uint8 values.  Returns numpy
         (y_dec, y_syn, x_dec, x_with_si, bpp) like src/AE.py:148.  The returned arrays are views of
         pinned staging buffers that are recycled two calls later.  The copy-out of y_dec/x_dec runs on
-        a side stream while the SI-Finder and SI-Net are still computing.  With `use_cuda_graph` (default) the step is replayed from two CUDA graphs captured on the first call
+        a side stream while the SI-Finder is computing, that of y_syn while the SI-Net is.  With `use_cuda_graph` (default) the step is replayed from three CUDA graphs captured on the first call
         with this input shape (`use_cuda_graph = False` launches eagerly)."""
         xs, ys = self._stage(x, "x"), self._stage(y, "y")
         self._ring ^= 1
@@ -363,45 +392,47 @@ class AE(object):
 
         overlap = self.e2e_overlap
 
-        def on_decoded(dec):
-            buf = self._pinned_out("dec", dec.shape, dec.dtype)
-            if not overlap:
-                early["dev"] = dec
-                early["dec"] = buf
-                return
-            self._copy_stream.wait_stream(main)
-            with torch.cuda.stream(self._copy_stream):
-                buf.copy_(dec, non_blocking=True)
-            if not self.use_cuda_graph:  # graph outputs are static buffers; both streams are joined below
-                dec.record_stream(self._copy_stream)
-            early["dec"] = buf
+        def copy_out(name):
+            """-> a hook that copies a finished segment's output to its pinned buffer on the side stream."""
+            def hook(t):
+                buf = self._pinned_out(name, t.shape, t.dtype)
+                early[name] = buf
+                if not overlap:
+                    late.append((buf, t))
+                    return
+                self._copy_stream.wait_stream(main)
+                with torch.cuda.stream(self._copy_stream):
+                    buf.copy_(t, non_blocking=True)
+                if not self.use_cuda_graph:  # graph outputs are static buffers; both streams are joined below
+                    t.record_stream(self._copy_stream)
+            return hook
 
+        late = []
+        on_decoded, on_found = copy_out("dec"), copy_out("y_syn")
         if self.use_cuda_graph:
             st = self._graph_state(B, xs.shape[2], xs.shape[3])
             st["x"].copy_(xs)  # uint8 -> fp32 conversion on the device, into the captured input buffers
             st["y"].copy_(ys)
             xd = st["x"]
+            out = dict(st["out"])
             st["g_head"].replay()
-            on_decoded(st["head"]["dec"])
-            st["g_tail"].replay()
-            out = dict(st["head"])
-            out.update(st["tail"])
+            on_decoded(out["dec"])
+            st["g_find"].replay()
+            on_found(out["y_syn"])
+            st["g_net"].replay()
         else:
             xd, yd = xs.to(torch.float32), ys.to(torch.float32)
-            out = self.reconstruct_device(xd, yd, on_decoded=on_decoded)
-        if "dev" in early:
-            early["dec"].copy_(early["dev"], non_blocking=True)
-        tail = []
-        for name in ("y_syn", "x_with_si"):
-            buf = self._pinned_out(name, out[name].shape, out[name].dtype)
-            buf.copy_(out[name], non_blocking=True)
-            tail.append(buf)
+            out = self.reconstruct_device(xd, yd, on_decoded=on_decoded, on_found=on_found)
+        for buf, t in late:
+            buf.copy_(t, non_blocking=True)
+        last = self._pinned_out("x_with_si", out["x_with_si"].shape, out["x_with_si"].dtype)
+        last.copy_(out["x_with_si"], non_blocking=True)
         bpp = bits.bitcost_to_bpp(out["bits"], xd)  # reads the fp64 bit sums (synchronises `main`)
         main.synchronize()
         self._copy_stream.synchronize()
         dec_host = early["dec"].numpy()
         self.last = out
-        return dec_host[:B], tail[0].numpy(), dec_host[B:], tail[1].numpy(), bpp
+        return dec_host[:B], early["y_syn"].numpy(), dec_host[B:], last.numpy(), bpp
 
     # ------------------------------------------------------------------ real bitstreams (SURVEY 8f N3)
     def compress(self, x, nstreams=8):
