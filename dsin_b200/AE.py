@@ -87,11 +87,14 @@ class AE(object):
         self._pinned = {}
         self._ring = 0
         self._copy_stream = None
+        self._in_stream = None
+        self._dev_in = {}
         self.last = {}
         # CUDA graphs for the numpy entry points: one capture per input shape, replayed afterwards, so a call
         # costs two graph launches instead of ~230 kernel launches (batch 1 is launch-bound otherwise)
         self.use_cuda_graph = True  # set to False for eager launches (tests compare the two)
         self.e2e_overlap = True     # copy y_dec/x_dec out on a side stream while the SI-Finder / SI-Net run
+        self.e2e_chunk = 8          # numpy calls with more pairs than this run as a pipeline of chunks of this many
         self._graphs = {}
 
     # ------------------------------------------------------------------ weights
@@ -381,7 +384,13 @@ class AE(object):
         (y_dec, y_syn, x_dec, x_with_si, bpp) like src/AE.py:148.  The returned arrays are views of
         pinned staging buffers that are recycled two calls later.  The copy-out of y_dec/x_dec runs on
         a side stream while the SI-Finder is computing, that of y_syn while the SI-Net is.  With `use_cuda_graph` (default) the step is replayed from three CUDA graphs captured on the first call
-        with this input shape (`use_cuda_graph = False` launches eagerly)."""
+        with this input shape (`use_cuda_graph = False` launches eagerly).  A batch of more than `e2e_chunk` pairs (a
+        multiple of it) is processed as a software pipeline of chunks: host staging and H2D of chunk k+1 and the D2H of
+        chunk k-1 overlap the kernels of chunk k (pairs are independent, so the results do not depend on the chunking)."""
+        c = self.e2e_chunk
+        if (self.use_cuda_graph and self.e2e_overlap and c and not torch.is_tensor(x) and not torch.is_tensor(y)
+                and x.shape[0] > c and x.shape[0] % c == 0):
+            return self._get_reconstructed_pipelined(np.ascontiguousarray(x), np.ascontiguousarray(y), int(c))
         xs, ys = self._stage(x, "x"), self._stage(y, "y")
         self._ring ^= 1
         main = torch.cuda.current_stream()
@@ -433,6 +442,95 @@ class AE(object):
         dec_host = early["dec"].numpy()
         self.last = out
         return dec_host[:B], early["y_syn"].numpy(), dec_host[B:], last.numpy(), bpp
+
+    def _get_reconstructed_pipelined(self, x, y, c):
+        """siNet_get_reconstructed for B = k * c pairs as a pipeline of k chunks of c pairs over three streams: `ins`
+        (H2D of the next chunk), the current stream (the three captured graphs of a chunk + a device copy of each
+        finished output into a private buffer), `cs` (D2H from the private buffers).  Events order the buffer reuse: an
+        input slot is refilled only after the chunk that used it has converted it, a private output buffer is rewritten
+        only after its previous D2H has finished.  Nothing blocks the host until the final synchronisation."""
+        B, _, H, W = x.shape
+        self._ring ^= 1
+        main = torch.cuda.current_stream()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        if self._in_stream is None:
+            self._in_stream = torch.cuda.Stream()
+        cs, ins = self._copy_stream, self._in_stream
+        st = self._graph_state(c, H, W)
+        out = st["out"]
+        px = self._pinned_out("in_x", x.shape, torch.from_numpy(x[:0]).dtype)
+        py = self._pinned_out("in_y", y.shape, torch.from_numpy(y[:0]).dtype)
+        f32 = torch.float32
+        host = {k: self._pinned_out(k, (B, 3, H, W), f32) for k in ("y_dec", "y_syn", "x_dec", "x_with_si")}
+        key = (c, H, W, px.dtype, py.dtype)
+        slots = self._dev_in.get(key)
+        if slots is None:
+            slots = [(torch.empty((c, 3, H, W), dtype=px.dtype, device=self.device),
+                      torch.empty((c, 3, H, W), dtype=py.dtype, device=self.device)) for _ in range(2)]
+            self._dev_in[key] = slots
+        small = {k: torch.empty((B,) + tuple(out[k].shape[1:]), dtype=out[k].dtype, device=self.device)
+                 for k in ("symbols", "symbols_y", "row", "col", "bits_sum", "best") if torch.is_tensor(out.get(k))}
+        # D2H sources: private device buffers, two per output.  The graphs' own output tensors cannot be read by a copy
+        # that overlaps the NEXT chunk: the three graphs share one memory pool, so e.g. x_with_si may occupy memory that
+        # the first graph uses for an intermediate activation.
+        okey = ("pipe_out", c, H, W)
+        priv = self._dev_in.get(okey)
+        if priv is None:
+            priv = [{"dec": torch.empty_like(out["dec"]), "y_syn": torch.empty_like(out["y_syn"]),
+                     "x_with_si": torch.empty_like(out["x_with_si"])} for _ in range(2)]
+            self._dev_in[okey] = priv
+        ins.wait_stream(main)  # the input slots may still be read by work the caller enqueued
+        consumed = [None, None]   # per input slot: the chunk that used it has converted it
+        drained = [{}, {}]        # per private output buffer: its D2H has finished
+        for k in range(B // c):
+            sl = slice(k * c, (k + 1) * c)
+            _host_copy(px[sl], x[sl])
+            _host_copy(py[sl], y[sl])
+            dx, dy = slots[k % 2]
+            if consumed[k % 2] is not None:
+                ins.wait_event(consumed[k % 2])
+            with torch.cuda.stream(ins):
+                dx.copy_(px[sl], non_blocking=True)
+                dy.copy_(py[sl], non_blocking=True)
+                arrived = torch.cuda.Event()
+                arrived.record(ins)
+            main.wait_event(arrived)
+            st["x"].copy_(dx)  # uint8 -> fp32 conversion on the device, into the captured input buffers
+            st["y"].copy_(dy)
+            consumed[k % 2] = torch.cuda.Event()
+            consumed[k % 2].record(main)
+            for seg, name in (("g_head", "dec"), ("g_find", "y_syn"), ("g_net", "x_with_si")):
+                st[seg].replay()
+                if seg == "g_head":
+                    for kk, t in small.items():
+                        if kk in ("symbols", "symbols_y", "bits_sum"):
+                            t[sl].copy_(out[kk])
+                elif seg == "g_find":
+                    for kk, t in small.items():
+                        if kk in ("row", "col", "best"):
+                            t[sl].copy_(out[kk])
+                src = priv[k % 2][name]
+                if name in drained[k % 2]:
+                    main.wait_event(drained[k % 2][name])  # chunk k-2's D2H of this buffer (long finished)
+                src.copy_(out[name])
+                ready = torch.cuda.Event()
+                ready.record(main)
+                cs.wait_event(ready)
+                with torch.cuda.stream(cs):
+                    if name == "dec":
+                        host["y_dec"][sl].copy_(src[:c], non_blocking=True)
+                        host["x_dec"][sl].copy_(src[c:], non_blocking=True)
+                    else:
+                        host[name][sl].copy_(src, non_blocking=True)
+                    drained[k % 2][name] = torch.cuda.Event()
+                    drained[k % 2][name].record(cs)
+        main.synchronize()
+        cs.synchronize()
+        num_bits = float(small["bits_sum"].sum().item())
+        bpp = np.float32(num_bits / float(B * H * W))  # bits.bitcost_to_bpp over the whole batch
+        self.last = small
+        return host["y_dec"].numpy(), host["y_syn"].numpy(), host["x_dec"].numpy(), host["x_with_si"].numpy(), bpp
 
     # ------------------------------------------------------------------ real bitstreams (SURVEY 8f N3)
     def compress(self, x, nstreams=8):
