@@ -53,17 +53,21 @@ class SiNet(object):
         self._first_padded = ops.ConvLayer(w1, None, W[S + "g_conv1/biases"], dilation=1, act=ops.ACT_LRELU02,
                                            device=self.device)
         self._tc_first = None
-        # even dilations: "pixel pair" form.  The NHWC tensor (n,H,W,32) is viewed as (n,H,W/2,64); a tap at
-        # x offset +-d becomes +-d/2 pairs, and the 32x32 weight slab becomes a block-diagonal 64x64 one
-        # (pixel parity is preserved by an even shift).  Twice the MMA work (on zeros) but half the TMA rows,
-        # which is what bounds these layers.
+        # the pixel-pair form of the nine 3x3 layers (only used with BAND = False, see _pair_form) is built on demand
+        self._w1_padded, self._variables = w1, W
         self._pair = {}
-        for i, rate in enumerate(self.RATES):
-            sc = S + "g_conv%d" % (i + 1)
-            w = w1 if i == 0 else np.asarray(W[sc + "/weights"], np.float32)  # layer 0: cin padded to 32
-            b = np.asarray(W[sc + "/biases"], np.float32)
-            self._pair[i] = self._pair_layer(w, b, rate)
         self._pair_tc = {}
+
+    def _pair_form(self, li):
+        """Even dilations in "pixel pair" form: the NHWC tensor (n,H,W,32) is viewed as (n,H,W/2,64); a tap at x offset
+        +-d becomes +-d/2 pairs, and the 32x32 weight slab becomes a block-diagonal 64x64 one (pixel parity is preserved
+        by an even shift).  Twice the MMA work (on zeros) but half the TMA rows, which is what bounds the tap-streaming
+        kernel on these layers."""
+        if li not in self._pair:
+            sc = synth.SIN + "g_conv%d" % (li + 1)
+            w = self._w1_padded if li == 0 else np.asarray(self._variables[sc + "/weights"], np.float32)
+            self._pair[li] = self._pair_layer(w, np.asarray(self._variables[sc + "/biases"], np.float32), self.RATES[li])
+        return self._pair[li]
 
     def _pair_layer(self, w, b, rate):
         """3x3 (32->32, dilation `rate`) conv re-expressed on pixel pairs: out parity p at pair j reads input
@@ -95,14 +99,14 @@ class SiNet(object):
         for li, tcl in enumerate([self._tc_first] + self._tc[:-1]):
             # dilation <= 4: the plain 32-channel layer runs on the halo-tile kernel (csrc/conv_h32.cu); larger
             # dilations on the row-band kernel (csrc/conv_dil.cu) -- both chosen by dsin_conv2d_tc from the geometry
-            if not BAND and use_pair and li in self._pair and self.RATES[li] > HALO_MAX_RATE:
+            if not BAND and use_pair and self.RATES[li] > HALO_MAX_RATE:
                 key = (li, PAIR_SHARED)
                 if key not in self._pair_tc:
                     rate = self.RATES[li]
                     if PAIR_SHARED and li >= 1 and rate % 2 == 0:  # parity-preserving: shared 32x32 slab
                         self._pair_tc[key] = ops.PairSharedTC(self._tc[li - 1], rate)
                     else:
-                        self._pair_tc[key] = ops.ConvTC(self._pair[li])
+                        self._pair_tc[key] = ops.ConvTC(self._pair_form(li))
                 v = tuple(None if t is None else t.view(n, hh, ww // 2, 64) for t in cur)
                 o = ops.conv_tc(v, self._pair_tc[key], terms=terms,
                                 prof=("tc%d_conv3x3_32to32_pair", 2.0 * n * hh * ww * 9 * (6 if li == 0 else 32) * 32))

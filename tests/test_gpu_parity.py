@@ -481,9 +481,10 @@ def test_cabi_error_codes_and_messages():
         h.check(rc)
 
 
-def test_sinet_pixel_pair_form_equals_plain_form():
-    """Even-dilation SI-Net layers in the pixel-pair form (W/2 x 64 'channels', block-diagonal weights) vs the
-    plain 32-channel tensor-core form, and both vs the oracle."""
+def test_sinet_layer_forms_agree():
+    """The three forms of the SI-Net's large-dilation layers -- row-band kernel (the product), tap streaming in the
+    pixel-pair view (W/2 x 64 'channels', block-diagonal weights) and plain tap streaming -- against each other and
+    against the oracle."""
     from dsin_b200 import siNet as sn
     Wt = calibrated_weights(0)
     ae = make_ae(120, 288, Wt)
@@ -492,15 +493,16 @@ def test_sinet_pixel_pair_form_equals_plain_form():
     ys = np.clip(rng.normal(110, 60, (2, 3, 120, 288)), 0, 255).astype(np.float32)
     ref = O.denormalize(O.si_net(torch.cat([O.normalize(torch.tensor(xd)), O.normalize(torch.tensor(ys))], 1), Wt))
     outs = {}
-    old = sn.PAIR
+    old = sn.BAND, sn.PAIR
     try:
-        for pair in (True, False):
-            sn.PAIR = pair
-            outs[pair] = ae._siNet.fused(_nhwc(_dev(xd)), _nhwc(_dev(ys))).cpu()
+        for form, (band, pair) in (("band", (True, True)), ("pair", (False, True)), ("plain", (False, False))):
+            sn.BAND, sn.PAIR = band, pair
+            outs[form] = ae._siNet.fused(_nhwc(_dev(xd)), _nhwc(_dev(ys))).cpu()
     finally:
-        sn.PAIR = old
-    assert float((outs[True] - outs[False]).abs().max()) < 2e-3
-    assert float((outs[True] - ref).abs().max()) < 2e-2
+        sn.BAND, sn.PAIR = old
+    assert float((outs["band"] - outs["pair"]).abs().max()) < 2e-3
+    assert float((outs["band"] - outs["plain"]).abs().max()) < 2e-3
+    assert float((outs["band"] - ref).abs().max()) < 2e-2
 
 
 def test_decode_side_region_equals_full_path():
