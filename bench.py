@@ -249,6 +249,8 @@ def run_ours(args, rank, world, local_rank):
     from dsin_b200.dist import gather_metrics, shard_range
     pk = peaks()
     ae = build_ae(local_rank, precision=args.precision)
+    if getattr(args, "e2e_chunk", None):
+        ae.e2e_chunk = args.e2e_chunk
     dev = torch.device("cuda", local_rank)
 
     # ---------------- which pairs this rank processes per step ----------------
@@ -460,7 +462,7 @@ def run_ours(args, rank, world, local_rank):
                    "timed_region": "K x (replays of the three CUDA graphs per micro-batch), inputs copied device-to-device"},
         "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms_max / args.steps,
-                "inputs": "plain numpy uint8 arrays (pageable), staged through pinned buffers inside the timed call; one call per micro-batch, which the call itself runs as a pipeline of 8-pair chunks (staging / H2D / kernels / D2H overlap)"},
+                "inputs": "plain numpy uint8 arrays (pageable), staged through pinned buffers inside the timed call; one call per micro-batch, which the call itself runs as a pipeline of %d-pair chunks when it holds more (staging / H2D / kernels / D2H overlap)" % ae.e2e_chunk},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
@@ -725,6 +727,7 @@ def main():
     ap.add_argument("--precision", default=None, help="precision policy name (dsin_b200/precision.py); default: shipped")
     ap.add_argument("--hw", default=None, help="geometry HxW other than 320x1224 (the metric string then says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=None, help="AE.e2e_chunk for the end-to-end calls (default: the AE's)")
     ap.add_argument("--streams", type=int, default=8, help="range-coder streams per image (--workload codec)")
     ap.add_argument("--workload", default="full", choices=["full", "sif", "enc", "codec", "roundtrip"],
                     help="full = configs[4] / configs[1]; sif = configs[2] (SI-Finder in isolation, --batch 32); "
