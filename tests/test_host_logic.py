@@ -3,6 +3,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 from dsin_b200 import config_parser, synth
 
@@ -112,3 +113,27 @@ def test_bitstream_header_is_validated_before_allocation():
     ok = bitstream.pack([b"\x00" * 70000] + [b"\x00"] * 7, 32, 40, 153, 6)
     with pytest.raises(ValueError, match="longer than"):
         pc.decode_symbols([ok], None, expect_shape=(32, 40, 153))
+
+
+def test_host_staging_copy_matches_numpy_assignment():
+    """AE._host_copy: the 8-byte-word fast path (torch's threaded copy) and the numpy fallback give the same bytes, for
+    whole buffers and for the per-chunk slices the pipelined entry point stages."""
+    from dsin_b200.AE import _host_copy
+    rng = np.random.default_rng(9)
+    old = torch.get_num_threads()
+    try:
+        for threads in (1, 2):
+            torch.set_num_threads(threads)
+            for shape, dt in (((16, 3, 320, 1224), np.uint8), ((3, 3, 37, 41), np.uint8), ((8, 3, 80, 144), np.float32)):
+                a = rng.integers(0, 256, size=shape).astype(dt)
+                dst = torch.zeros(shape, dtype=torch.from_numpy(a[:0]).dtype)
+                _host_copy(dst, a)
+                assert np.array_equal(dst.numpy(), a)
+                if shape[0] % 2 == 0:
+                    dst.zero_()
+                    h = shape[0] // 2
+                    for sl in (slice(0, h), slice(h, shape[0])):
+                        _host_copy(dst[sl], a[sl])
+                    assert np.array_equal(dst.numpy(), a)
+    finally:
+        torch.set_num_threads(old)
