@@ -174,6 +174,7 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int et = (warp - 2) * 32 + lane;  // 0..255 among epilogue threads
+    const float kstep = p.use_mask ? ex2_approx(2.f * p.kw) : 1.f;
     int it = 0;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const int img = u / units_per_img, r = u % units_per_img;
@@ -186,7 +187,9 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       int bi0 = -1, bi1 = -1, bi2 = -1, bi3 = -1;
       const int i1 = min(p.hp, (rg + 1) * ROWS_PER_UNIT);
       for (int i = rg * ROWS_PER_UNIT; i < i1; ++i) {
-        float rowf = pi.y;  // rsqrt(den_x) * row factor of the prior
+        // rsqrt(den_x) * row factor of the prior; NaN for a lane without a patch: every score of it is NaN, NaN never
+        // passes a comparison and fmaxf ignores it
+        float rowf = pvalid ? pi.y : __int_as_float(0x7fc00000);
         if (p.use_mask) {
           float dh = (float)i - pi.z;
           rowf *= ex2_approx(p.kh * dh * dh);
@@ -195,14 +198,16 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           const int acc = it & 1;
           const int j0 = jt * TN;
           const int nvalid = min(TN, p.wp - j0);
-          // stage per-position statistics for this tile (double buffered with the accumulator)
+          // stage per-position statistics for this tile (double buffered with the accumulator): mean_y and
+          // rsqrt(den_y); NaN for a position past the row end and for a flat window (den_y <= 0: NaN / inf in the exact
+          // arithmetic, never a candidate)
           float2* sp = s_pos + acc * TN;
           {
-            float2 v = make_float2(0.f, 0.f);
+            float2 v = make_float2(0.f, __int_as_float(0x7fc00000));
             if (et < nvalid) {
               float4 ys = __ldg(p.ystat + ((size_t)img * p.hp + i) * p.wp + j0 + et);
               v.x = ys.y;
-              v.y = ys.z > 0.f ? rsqrtf(ys.z) : 0.f;
+              v.y = ys.z > 0.f ? rsqrtf(ys.z) : __int_as_float(0x7fc00000);
             }
             sp[et] = v;
           }
@@ -215,21 +220,41 @@ sif_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             if (cb >= nvalid) break;  // warp-uniform
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + cb), v);
+            // column factor of the prior by recurrence: g(c) = 2^(kw (c - cx)^2), g(c+1) = g(c) r(c),
+            // r(c+1) = r(c) 2^(2 kw) -- two multiplications per position instead of an ex2 (the coarse score only has to
+            // be good to ~1e-4; 32 steps of fp32 rounding stay below 1e-5 relative)
+            float g0 = rowf, r0 = 1.f;
+            if (p.use_mask) {
+              const float dw = (float)(j0 + cb) - pi.w;
+              g0 = rowf * ex2_approx(p.kw * dw * dw);
+              r0 = ex2_approx(p.kw * (2.f * dw + 1.f));
+            }
             tmem_ld_wait();
+            // pass 1, branch-free: the chunk's best score
+            float m = -INFINITY;
+            {
+              float g = g0, r = r0;
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-              const int c = cb + jj;
-              const float2 ps = sp[c];
-              float s = (__uint_as_float(v[jj]) - ps.x * pi.x) * ps.y * rowf;
-              if (p.use_mask) {
-                float dw = (float)(j0 + c) - pi.w;
-                s *= ex2_approx(p.kw * dw * dw);
+              for (int jj = 0; jj < 32; ++jj) {
+                const float2 ps = sp[cb + jj];
+                const float s = (__uint_as_float(v[jj]) - ps.x * pi.x) * ps.y * g;
+                m = fmaxf(m, s);
+                g *= r;
+                r *= kstep;
               }
-              // a flat window (den_y <= 0: ps.y == 0) is NaN / inf in the exact arithmetic and is never a candidate
-              const bool pass = pvalid && c < nvalid && ps.y > 0.f && s > bs3;
-              if (__any_sync(0xffffffffu, pass)) {  // rare after warm-up; the branch is warp-uniform
-                if (pass) {  // strict >: among equal scores the earlier position stays ahead
-                  const int idx = i * p.wp + j0 + c;
+            }
+            // pass 2, rare after warm-up: some lane has a score above its group's 4th best -- insert in order with
+            // the same arithmetic (strict >: among equal scores the earlier position stays ahead)
+            if (__any_sync(0xffffffffu, m > bs3)) {
+              float g = g0, r = r0;
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) {
+                const float2 ps = sp[cb + jj];
+                const float s = (__uint_as_float(v[jj]) - ps.x * pi.x) * ps.y * g;
+                g *= r;
+                r *= kstep;
+                if (s > bs3) {
+                  const int idx = i * p.wp + j0 + cb + jj;
                   if (s > bs0) {
                     bs3 = bs2; bi3 = bi2; bs2 = bs1; bi2 = bi1; bs1 = bs0; bi1 = bi0; bs0 = s; bi0 = idx;
                   } else if (s > bs1) {
