@@ -7,7 +7,8 @@ the model (`<cwd>/weights/<load_model_name>/model`, a TF-V2 checkpoint, when the
 `--weights` overrides it and also accepts an .npz), and for every test pair call ``siNet_get_reconstructed``,
 clip, save the PNG and optionally append to the loss lists.  Pairs come from the reference's pair lists
 (`<cwd>/data_paths/<file_path_test>` through DataProvider.Dataset), or from ``--synthetic N`` (seeded
-generator) or ``--pairs x.npy y.npy`` arrays shaped (N,3,H,W).  Training flags in the config are ignored.
+generator) or ``--pairs x.npy y.npy`` arrays shaped (N,3,H,W).  ``--validate`` adds the validation step of the
+reference's training loop (mean ``siNet_validate`` loss); the training flags in the config are ignored.
 """
 from __future__ import annotations
 
@@ -68,6 +69,19 @@ def main(run_dict, args):
         _val_names, test_names = data.get_data_size()
         n_test = len(test_names)
         batches = (data.get_data_for_test() for _ in range(n_test))
+    if args.validate:  # the validation step of the reference's training loop (src/main.py:64-73), on its own
+        if args.pairs or args.synthetic:
+            val_batches = [[xs[i:i + 1], ys[i:i + 1]] for i in range(xs.shape[0])]
+        else:
+            val_names, _test_names = data.get_data_size()
+            val_batches = (data.get_data_for_val() for _ in range(len(val_names) // run_dict["batch_size"]))
+        val_sum, val_iterations = 0.0, 0
+        for x_val, y_val in val_batches:
+            val_sum += ae.siNet_validate(x_val, y_val)
+            val_iterations += 1
+        val_loss = val_sum / float(max(val_iterations, 1))
+        print("validation loss = {:.6f} over {:d} batches".format(val_loss, val_iterations))
+        run_dict["val_loss"] = val_loss
     results = []
     root_save_img = run_dict["root_save_img"]
     if not root_save_img.endswith(os.sep):
@@ -119,6 +133,9 @@ def build_parser():
     parser.add_argument("--save_dir", type=str, default=None, help="image / list output root (default <cwd>/images/)")
     parser.add_argument("--no_save_test_img", action="store_true", help="reference default is to save (main.py:203)")
     parser.add_argument("--create_loss_list", action="store_true", help="append per-image metric lists (main.py:206)")
+    parser.add_argument("--validate", action="store_true",
+                        help="first report the mean validation loss (AE.siNet_validate, src/main.py:64-73) over the "
+                             "validation split (or over the --synthetic / --pairs images)")
     parser.add_argument("--real_bpp", action="store_true",
                         help="also range-code the symbols (PC1 bitstream) and report / save the real size")
     return parser

@@ -137,3 +137,10 @@ def test_host_staging_copy_matches_numpy_assignment():
                     assert np.array_equal(dst.numpy(), a)
     finally:
         torch.set_num_threads(old)
+
+
+def test_main_parser_has_the_validation_step_switch():
+    from dsin_b200 import main as dmain
+    a = dmain.build_parser().parse_args(["--validate", "--synthetic", "2", "--no_save_test_img"])
+    assert a.validate and a.synthetic == 2 and a.no_save_test_img
+    assert not dmain.build_parser().parse_args([]).validate
